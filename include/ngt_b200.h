@@ -1,0 +1,140 @@
+/*
+ * ngt_b200.h — C ABI of the B200-native New Graph Transformation (NGT) engine.
+ *
+ * This is the drop-in boundary for ONE hot path of js850/kmc_rates: phase-1 node elimination
+ * (P_uv += P_ux P_xv/(1-P_xx), tau_u += P_ux tau_x/(1-P_xx)) + the phase-2 per-a reduction ->
+ * k_AB, k_BA, steady-state rates, committors.  Every entry point replaces a call the reference's
+ * Cython binding makes into its C++ engine; a maintainer binds these instead.
+ *
+ *   entry point                          replaces (reference file:line)
+ *   ----------------------------------   -----------------------------------------------------------
+ *   ngt_create                           new cNGT(rate_map, A, B)            kmc_rates/ngt.pyx:93
+ *                                        graph_ns::NGT::NGT(rate_map_t&,..)  source/kmc_rates/ngt.hpp:105-181
+ *   ngt_create_dense / _dense_dev        same ctor for a complete rate matrix (no std::map)
+ *   ngt_set_weights                      set_node_occupation_probabilities   ngt.pyx:105, ngt.hpp:183-185
+ *   ngt_compute_rates                    compute_rates()                     ngt.pyx:119, ngt.hpp:436-439
+ *   ngt_compute_rates_and_committors     compute_rates_and_committors()      ngt.pyx:129, ngt.hpp:616-630
+ *   ngt_get_rates                        get_rate_AB/BA/AB_SS/BA_SS          ngt.pyx:132-146, ngt.hpp:463-513
+ *   ngt_get_final                        final_omPxx / final_tau             ngt.hpp:45-53
+ *   ngt_get_committors                   get_committors()                    ngt.pyx:148-154, ngt.hpp:98
+ *   ngt_get_reduced                      the A∪B graph left in NGT::_graph   ngt.hpp:36 (GraphReduction.graph,
+ *                                                                            kmc_rates/_kmc_rates.py:127-131)
+ *   ngt_destroy                          del thisptr                         ngt.pyx:111-114
+ *   ngt_batch_*                          a loop of the above over networks that share one topology
+ *
+ * Conventions: nodes are dense ids 0..n-1 (label -> id mapping stays on the host side, as in
+ * ngt.pyx:68-73); plain pointers and sizes only; the caller owns every buffer; every call is
+ * synchronous on return; every function returns 0 on success or an NGT_E_* code, with a message in
+ * ngt_last_error().  There is NO CPU fallback: without a CUDA device every compute call fails with
+ * NGT_E_CUDA.
+ */
+#ifndef NGT_B200_H_
+#define NGT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ngt_handle_s *ngt_handle;
+
+enum {
+    NGT_OK = 0,
+    NGT_E_INVALID = 1,   /* bad argument: id out of range, A∩B≠∅, empty A or B, node without out-rates */
+    NGT_E_CUDA = 2,      /* CUDA runtime error (no device, out of memory, launch failure) */
+    NGT_E_STATE = 3,     /* call order: results requested before compute_* */
+    NGT_E_NUMERIC = 4    /* a pivot 1-P_xx was zero or not finite (dead-end node) */
+};
+
+/* Options (0 = default everywhere). */
+typedef struct ngt_options {
+    int32_t device;          /* CUDA device ordinal */
+    int32_t gemm_path;       /* 0 = FP64 tensor-core DMMA (default), 1 = scalar DFMA (debug / cross-check) */
+    int32_t leaf_size;       /* nested-dissection leaf size (0 -> 64) */
+    int32_t keep_factor;     /* 1 = keep eliminated rows for committor back-substitution */
+    int32_t phase2_closed_form; /* 1 = also evaluate phase 2 by the closed form 1/G_aa as a cross-check */
+    int32_t reserved[11];
+} ngt_options;
+
+/* ---- construction ------------------------------------------------------------------------- */
+
+/* Sparse network from COO rate constants k[e] : src[e] -> dst[e] (host pointers).  A duplicate (src,dst)
+ * overwrites the earlier one, as the reference's std::map does.  Does ingest + ordering + symbolic analysis. */
+int ngt_create(int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, const double *k,
+               int64_t nA, const int64_t *A, int64_t nB, const int64_t *B,
+               const ngt_options *opt, ngt_handle *out);
+
+/* Complete network from a dense row-major n x n rate matrix K (K[u*n+v] = k_uv, diagonal = self rate,
+ * usually 0).  K is a HOST pointer for ngt_create_dense and a DEVICE pointer for ngt_create_dense_dev. */
+int ngt_create_dense(int64_t n, const double *K_host, int64_t nA, const int64_t *A, int64_t nB, const int64_t *B,
+                     const ngt_options *opt, ngt_handle *out);
+int ngt_create_dense_dev(int64_t n, const double *K_dev, int64_t nA, const int64_t *A, int64_t nB, const int64_t *B,
+                         const ngt_options *opt, ngt_handle *out);
+
+/* Replace the rate constants of an existing handle, keeping topology, ordering and symbolic analysis
+ * (temperature / rate sweeps).  k has the length and order given at creation.  Host or device pointer. */
+int ngt_set_rates(ngt_handle h, const double *k_host);
+int ngt_set_rates_dev(ngt_handle h, const double *k_dev);
+
+int ngt_set_weights(ngt_handle h, int64_t nw, const int64_t *ids, const double *w);
+
+void ngt_destroy(ngt_handle h);
+
+/* ---- compute ------------------------------------------------------------------------------ */
+int ngt_compute_rates(ngt_handle h);
+int ngt_compute_rates_and_committors(ngt_handle h);
+/* phase 1 only (device resident; no result download) — used by bench.py for the HBM-resident timing */
+int ngt_phase_one(ngt_handle h);
+int ngt_phase_two(ngt_handle h);
+
+/* ---- results ------------------------------------------------------------------------------ */
+int ngt_get_rates(ngt_handle h, double out4[4]);                 /* k_AB, k_BA, k_AB^SS, k_BA^SS */
+int ngt_get_final(ngt_handle h, double *omPxx, double *tau);      /* |A|+|B| each, A then B in the order passed */
+int ngt_get_reduced(ngt_handle h, double *P, double *tau);        /* (|A|+|B|)^2 row-major, |A|+|B| */
+int ngt_get_initial_tau(ngt_handle h, double *tau);               /* n */
+int ngt_get_committors(ngt_handle h, double *q);                  /* n; q_A = 0, q_B = 1 */
+int ngt_get_mfpt(ngt_handle h, double *t);                        /* n; mean first-passage time to A∪B */
+
+/* ---- statistics for roofline accounting --------------------------------------------------- */
+typedef struct ngt_stats {
+    int64_t n_nodes, n_rates, n_eliminated;
+    int64_t n_fronts, n_levels, n_launches;
+    int64_t max_front, pool_doubles;
+    double  alg_flops;          /* sum over eliminated nodes of 2 d_in d_out + 3 d_in + d_out */
+    double  alg_bytes;          /* sum of 16 d_in d_out + 12 (d_in+d_out) + 16 d_in + 8 */
+    double  schur_flops;        /* flops issued by the Schur-update GEMM kernel */
+    double  ms_symbolic, ms_ingest, ms_phase1, ms_phase2, ms_schur;   /* last run; device times from CUDA events */
+    double  reserved[8];
+} ngt_stats;
+int ngt_get_stats(ngt_handle h, ngt_stats *st);
+
+/* ---- batched networks sharing one topology (temperature sweeps) --------------------------- */
+/* k is nbatch x nnz (row-major): network b uses k[b*nnz .. (b+1)*nnz). */
+int ngt_batch_create(int64_t nbatch, int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst,
+                     const double *k, int64_t nA, const int64_t *A, int64_t nB, const int64_t *B,
+                     const ngt_options *opt, ngt_handle *out);
+/* dense twin: K is nbatch x n x n, HOST or DEVICE pointer */
+int ngt_batch_create_dense(int64_t nbatch, int64_t n, const double *K_host, int64_t nA, const int64_t *A,
+                           int64_t nB, const int64_t *B, const ngt_options *opt, ngt_handle *out);
+int ngt_batch_create_dense_dev(int64_t nbatch, int64_t n, const double *K_dev, int64_t nA, const int64_t *A,
+                               int64_t nB, const int64_t *B, const ngt_options *opt, ngt_handle *out);
+/* rates: nbatch x 4 */
+int ngt_batch_get_rates(ngt_handle h, double *out);
+
+/* ---- multi-GPU phase 2: shard the per-a reductions ------------------ */
+/* Device pointer + size (doubles) of the reduced (|A|+|B|) x ld block incl. tau column, valid after
+ * ngt_phase_one; a rank broadcasts it with NCCL into the same buffer of its peers. */
+int ngt_reduced_block_dev(ngt_handle h, double **dptr, int64_t *ndoubles);
+/* Run the per-a reductions only for the a's with (index % nranks) == rank; unfilled entries of the
+ * omPxx/tau result are 0 so that an all-reduce(sum) or all-gather merges the shards. */
+int ngt_phase_two_shard(ngt_handle h, int32_t rank, int32_t nranks);
+int ngt_set_final(ngt_handle h, const double *omPxx, const double *tau);   /* install merged results */
+
+const char *ngt_last_error(void);
+const char *ngt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGT_B200_H_ */

@@ -1,0 +1,310 @@
+"""ctypes binding of the C ABI in include/ngt_b200.h (kmc_rates_b200/csrc/libngt_b200.so).
+
+This is the thin layer the north star asks for: Python host code -> C ABI -> hand-written sm_100a
+kernels.  It plays the role of the reference's Cython shim (reference kmc_rates/ngt.pyx:12-28: the
+`cdef extern` block and `except +` error translation).  There is no fallback: if the library is not
+built, or no CUDA device is present, calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libngt_b200.so")
+
+NGT_OK, NGT_E_INVALID, NGT_E_CUDA, NGT_E_STATE, NGT_E_NUMERIC = 0, 1, 2, 3, 4
+
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_f64p = ctypes.POINTER(ctypes.c_double)
+
+
+class Options(ctypes.Structure):
+    _fields_ = [
+        ("device", ctypes.c_int32),
+        ("gemm_path", ctypes.c_int32),
+        ("leaf_size", ctypes.c_int32),
+        ("keep_factor", ctypes.c_int32),
+        ("phase2_closed_form", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 11),
+    ]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [
+        ("n_nodes", ctypes.c_int64), ("n_rates", ctypes.c_int64), ("n_eliminated", ctypes.c_int64),
+        ("n_fronts", ctypes.c_int64), ("n_levels", ctypes.c_int64), ("n_launches", ctypes.c_int64),
+        ("max_front", ctypes.c_int64), ("pool_doubles", ctypes.c_int64),
+        ("alg_flops", ctypes.c_double), ("alg_bytes", ctypes.c_double), ("schur_flops", ctypes.c_double),
+        ("ms_symbolic", ctypes.c_double), ("ms_ingest", ctypes.c_double), ("ms_phase1", ctypes.c_double),
+        ("ms_phase2", ctypes.c_double), ("ms_schur", ctypes.c_double),
+        ("reserved", ctypes.c_double * 8),
+    ]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _t in self._fields_ if f != "reserved"}
+
+
+class NGTNumericError(ArithmeticError):
+    """a pivot 1-P_xx was zero / not finite (dead-end node)"""
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library.  Raises ImportError when it has not been built — there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "kmc_rates_b200: CUDA extension %s is missing. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    H = ctypes.c_void_p
+    HP = ctypes.POINTER(ctypes.c_void_p)
+    OP = ctypes.POINTER(Options)
+    i64, vp = ctypes.c_int64, ctypes.c_void_p
+    sig = {
+        "ngt_create": [i64, i64, _i64p, _i64p, vp, i64, _i64p, i64, _i64p, OP, HP],
+        "ngt_create_dense": [i64, vp, i64, _i64p, i64, _i64p, OP, HP],
+        "ngt_create_dense_dev": [i64, vp, i64, _i64p, i64, _i64p, OP, HP],
+        "ngt_set_rates": [H, vp],
+        "ngt_set_rates_dev": [H, vp],
+        "ngt_set_weights": [H, i64, _i64p, _f64p],
+        "ngt_compute_rates": [H],
+        "ngt_compute_rates_and_committors": [H],
+        "ngt_phase_one": [H],
+        "ngt_phase_two": [H],
+        "ngt_get_rates": [H, _f64p],
+        "ngt_get_final": [H, _f64p, _f64p],
+        "ngt_get_reduced": [H, _f64p, _f64p],
+        "ngt_get_initial_tau": [H, _f64p],
+        "ngt_get_committors": [H, _f64p],
+        "ngt_get_mfpt": [H, _f64p],
+        "ngt_get_stats": [H, ctypes.POINTER(Stats)],
+        "ngt_batch_create": [i64, i64, i64, _i64p, _i64p, vp, i64, _i64p, i64, _i64p, OP, HP],
+        "ngt_batch_create_dense": [i64, i64, vp, i64, _i64p, i64, _i64p, OP, HP],
+        "ngt_batch_create_dense_dev": [i64, i64, vp, i64, _i64p, i64, _i64p, OP, HP],
+        "ngt_batch_get_rates": [H, _f64p],
+        "ngt_reduced_block_dev": [H, ctypes.POINTER(vp), _i64p],
+        "ngt_phase_two_shard": [H, ctypes.c_int32, ctypes.c_int32],
+        "ngt_set_final": [H, _f64p, _f64p],
+    }
+    for name, args in sig.items():
+        f = getattr(L, name)
+        f.argtypes = args
+        f.restype = ctypes.c_int
+    L.ngt_destroy.argtypes = [H]
+    L.ngt_destroy.restype = None
+    L.ngt_last_error.restype = ctypes.c_char_p
+    L.ngt_version.restype = ctypes.c_char_p
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "ngt_create", "ngt_create_dense", "ngt_create_dense_dev", "ngt_set_rates", "ngt_set_rates_dev", "ngt_set_weights",
+    "ngt_destroy", "ngt_compute_rates", "ngt_compute_rates_and_committors", "ngt_phase_one", "ngt_phase_two",
+    "ngt_get_rates", "ngt_get_final", "ngt_get_reduced", "ngt_get_initial_tau", "ngt_get_committors", "ngt_get_mfpt",
+    "ngt_get_stats", "ngt_batch_create", "ngt_batch_create_dense", "ngt_batch_create_dense_dev", "ngt_batch_get_rates",
+    "ngt_reduced_block_dev", "ngt_phase_two_shard", "ngt_set_final", "ngt_last_error", "ngt_version",
+]
+
+
+def check(status):
+    """Translate a status code the way ngt.pyx's `except +` translates C++ exceptions."""
+    if status == NGT_OK:
+        return
+    msg = lib().ngt_last_error().decode("utf-8", "replace")
+    if status == NGT_E_INVALID:
+        raise ValueError(msg)
+    if status == NGT_E_NUMERIC:
+        raise NGTNumericError(msg)
+    raise RuntimeError(msg)
+
+
+def _ids(seq):
+    a = np.ascontiguousarray(list(seq), np.int64)
+    return a, a.ctypes.data_as(_i64p)
+
+
+def _is_torch_cuda(x):
+    return hasattr(x, "data_ptr") and hasattr(x, "is_cuda") and x.is_cuda
+
+
+class Handle(object):
+    """Owns one ngt_handle (like BaseNGT owns its cNGT*, reference ngt.pyx:62,93,111-114)."""
+
+    def __init__(self):
+        self.h = ctypes.c_void_p()
+        self._keep = []   # buffers that must outlive the handle (device tensors borrowed by the engine)
+        self.n = 0
+        self.nA = self.nB = 0
+        self.nbatch = 1
+
+    @staticmethod
+    def _opt(device=0, gemm_path=0, leaf_size=0):
+        o = Options()
+        o.device, o.gemm_path, o.leaf_size = int(device), int(gemm_path), int(leaf_size)
+        return o
+
+    @classmethod
+    def from_coo(cls, n, src, dst, k, A, B, nbatch=1, **opt):
+        self = cls()
+        src = np.ascontiguousarray(src, np.int64)
+        dst = np.ascontiguousarray(dst, np.int64)
+        k = np.ascontiguousarray(k, np.float64)
+        if k.size != src.size * nbatch or dst.size != src.size:
+            raise ValueError("src, dst, k have inconsistent lengths")
+        a, ap = _ids(A)
+        b, bp = _ids(B)
+        o = cls._opt(**opt)
+        L = lib()
+        if nbatch == 1:
+            st = L.ngt_create(int(n), src.size, src.ctypes.data_as(_i64p), dst.ctypes.data_as(_i64p),
+                              k.ctypes.data, a.size, ap, b.size, bp, ctypes.byref(o), ctypes.byref(self.h))
+        else:
+            st = L.ngt_batch_create(int(nbatch), int(n), src.size, src.ctypes.data_as(_i64p), dst.ctypes.data_as(_i64p),
+                                    k.ctypes.data, a.size, ap, b.size, bp, ctypes.byref(o), ctypes.byref(self.h))
+        check(st)
+        self.n, self.nA, self.nB, self.nbatch = int(n), a.size, b.size, int(nbatch)
+        return self
+
+    @classmethod
+    def from_dense(cls, K, A, B, **opt):
+        """K: (n, n) or (nbatch, n, n) rate matrix; numpy array (host) or torch CUDA float64 tensor (zero copy)."""
+        self = cls()
+        a, ap = _ids(A)
+        b, bp = _ids(B)
+        L = lib()
+        shape = tuple(K.shape)
+        if len(shape) == 2:
+            nbatch, n = 1, shape[0]
+        elif len(shape) == 3:
+            nbatch, n = shape[0], shape[1]
+        else:
+            raise ValueError("K must be (n, n) or (nbatch, n, n)")
+        if shape[-1] != n:
+            raise ValueError("K must be square")
+        if _is_torch_cuda(K):
+            import torch
+            if K.dtype != torch.float64:
+                raise ValueError("device rate matrix must be float64")
+            K = K.contiguous()
+            opt = dict(opt)
+            opt["device"] = K.device.index or 0
+            ptr, dev = ctypes.c_void_p(K.data_ptr()), True
+            self._keep.append(K)
+        else:
+            K = np.ascontiguousarray(K, np.float64)
+            ptr, dev = ctypes.c_void_p(K.ctypes.data), False
+            self._keep.append(K)
+        o = cls._opt(**opt)
+        if nbatch == 1:
+            fn = L.ngt_create_dense_dev if dev else L.ngt_create_dense
+            st = fn(int(n), ptr, a.size, ap, b.size, bp, ctypes.byref(o), ctypes.byref(self.h))
+        else:
+            fn = L.ngt_batch_create_dense_dev if dev else L.ngt_batch_create_dense
+            st = fn(int(nbatch), int(n), ptr, a.size, ap, b.size, bp, ctypes.byref(o), ctypes.byref(self.h))
+        check(st)
+        if not dev:
+            self._keep.clear()   # host data was copied to the device
+        self.n, self.nA, self.nB, self.nbatch = int(n), a.size, b.size, int(nbatch)
+        return self
+
+    def close(self):
+        if self.h:
+            lib().ngt_destroy(self.h)
+            self.h = ctypes.c_void_p()
+        self._keep = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setters
+    def set_rates(self, k):
+        if _is_torch_cuda(k):
+            k = k.contiguous()
+            self._keep = [k]
+            check(lib().ngt_set_rates_dev(self.h, ctypes.c_void_p(k.data_ptr())))
+        else:
+            k = np.ascontiguousarray(k, np.float64)
+            check(lib().ngt_set_rates(self.h, ctypes.c_void_p(k.ctypes.data)))
+
+    def set_weights(self, ids, w):
+        ids = np.ascontiguousarray(ids, np.int64)
+        w = np.ascontiguousarray(w, np.float64)
+        check(lib().ngt_set_weights(self.h, ids.size, ids.ctypes.data_as(_i64p), w.ctypes.data_as(_f64p)))
+
+    # ---- compute
+    def compute_rates(self):
+        check(lib().ngt_compute_rates(self.h))
+
+    def compute_rates_and_committors(self):
+        check(lib().ngt_compute_rates_and_committors(self.h))
+
+    def phase_one(self):
+        check(lib().ngt_phase_one(self.h))
+
+    def phase_two(self):
+        check(lib().ngt_phase_two(self.h))
+
+    def phase_two_shard(self, rank, nranks):
+        check(lib().ngt_phase_two_shard(self.h, int(rank), int(nranks)))
+
+    # ---- results
+    def rates(self):
+        out = np.zeros((self.nbatch, 4))
+        if self.nbatch == 1:
+            check(lib().ngt_get_rates(self.h, out.ctypes.data_as(_f64p)))
+            return out[0]
+        check(lib().ngt_batch_get_rates(self.h, out.ctypes.data_as(_f64p)))
+        return out
+
+    def final(self):
+        m = self.nA + self.nB
+        om, tau = np.zeros(m * self.nbatch), np.zeros(m * self.nbatch)
+        check(lib().ngt_get_final(self.h, om.ctypes.data_as(_f64p), tau.ctypes.data_as(_f64p)))
+        return om[:m], tau[:m]
+
+    def set_final(self, om, tau):
+        om = np.ascontiguousarray(om, np.float64)
+        tau = np.ascontiguousarray(tau, np.float64)
+        check(lib().ngt_set_final(self.h, om.ctypes.data_as(_f64p), tau.ctypes.data_as(_f64p)))
+
+    def reduced(self):
+        m = self.nA + self.nB
+        P, tau = np.zeros((m, m)), np.zeros(m)
+        check(lib().ngt_get_reduced(self.h, P.ctypes.data_as(_f64p), tau.ctypes.data_as(_f64p)))
+        return P, tau
+
+    def initial_tau(self):
+        t = np.zeros(self.n)
+        check(lib().ngt_get_initial_tau(self.h, t.ctypes.data_as(_f64p)))
+        return t
+
+    def committors(self):
+        q = np.zeros(self.n)
+        check(lib().ngt_get_committors(self.h, q.ctypes.data_as(_f64p)))
+        return q
+
+    def mfpt(self):
+        t = np.zeros(self.n)
+        check(lib().ngt_get_mfpt(self.h, t.ctypes.data_as(_f64p)))
+        return t
+
+    def stats(self):
+        s = Stats()
+        check(lib().ngt_get_stats(self.h, ctypes.byref(s)))
+        return s.as_dict()
+
+    def reduced_block_dev(self):
+        p = ctypes.c_void_p()
+        n = ctypes.c_int64()
+        check(lib().ngt_reduced_block_dev(self.h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value

@@ -1,0 +1,930 @@
+// C-ABI implementation (include/ngt_b200.h): handle, ingest, schedule of kernel launches, results.
+//
+// Host orchestration mirrors what the reference's NGT object does (reference source/kmc_rates/ngt.hpp):
+//   ctor (ngt.hpp:105-181)            -> ngt_create*: ids, A/B, symbolic analysis, device buffers
+//   phase_one (ngt.hpp:338-354)       -> Engine::phase_one: ingest kernel + per-level assembly + blocked elimination
+//   phase_two (ngt.hpp:362-431)       -> Engine::phase_two: one task front per a, same elimination kernels
+//   rate getters (ngt.hpp:444-513)    -> Engine::finish_rates (host arithmetic on |A|+|B| numbers)
+//   committors (ngt.hpp:518-630)      -> Engine::backsub (back-substitution over the kept factors)
+// There is no CPU compute path: every numeric step is a CUDA kernel from kernels.cu.
+#include "../../include/ngt_b200.h"
+#include "kernels.cuh"
+#include "symbolic.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+struct CudaError : std::runtime_error {
+    explicit CudaError(const std::string &m) : std::runtime_error(m) {}
+};
+struct InvalidError : std::runtime_error {
+    explicit InvalidError(const std::string &m) : std::runtime_error(m) {}
+};
+struct StateError : std::runtime_error {
+    explicit StateError(const std::string &m) : std::runtime_error(m) {}
+};
+struct NumericError : std::runtime_error {
+    explicit NumericError(const std::string &m) : std::runtime_error(m) {}
+};
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" +      \
+                            std::to_string(__LINE__) + ")");                                              \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void upload(const std::vector<T> &v) {
+        alloc(v.size());
+        if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+using ngt::DFront;
+using ngt::Symbolic;
+
+// One group of fronts eliminated by the same launches.
+struct HostBatch {
+    std::vector<int> ids;     // front ids
+    std::vector<int> f, k;    // their order and pivot count (for grid sizing)
+    size_t dev_off = 0;       // offset into the device id array
+    int max_k = 0;
+};
+
+struct Engine {
+    ngt_options opt{};
+    Symbolic S;
+    bool dense = false;
+    int nbatch = 1;
+    int64_t n = 0, nnz = 0;
+    std::vector<int64_t> A, B;
+    std::vector<double> weights;
+    bool have_weights = false;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+
+    // device: structure
+    DevBuf<DFront> d_fronts;
+    DevBuf<int> d_ids;              // batch ids (phase 1), then extend-add rounds
+    DevBuf<int> d_rel;
+    DevBuf<long long> d_rel_off;
+    DevBuf<int> d_fidx;
+    DevBuf<long long> d_idx_off;
+    std::vector<HostBatch> batches;
+    struct Round { int level; size_t dev_off; int count; int max_m; };
+    std::vector<Round> rounds;      // extend-add rounds, sorted by level of the PARENT
+    // device: values
+    DevBuf<double> d_pool;
+    long long pool_stride = 0;
+    DevBuf<double> d_wbuf;
+    int maxfb = 1;
+    DevBuf<int> d_err;
+    DevBuf<double> d_tau0;
+    // sparse ingest
+    DevBuf<long long> d_row_ptr, d_dest, d_tau_dest;
+    DevBuf<int> d_row_node, d_korig;
+    DevBuf<double> d_k;
+    int n_rows = 0;
+    // dense ingest
+    DevBuf<double> d_K_owned;
+    const double *d_K = nullptr;
+    DevBuf<int> d_pos;
+    // phase 2
+    DevBuf<double> d_p2pool;
+    long long p2_stride = 0;
+    DevBuf<DFront> d_p2fronts;
+    DevBuf<int> d_p2ids;
+    std::vector<HostBatch> p2batches[2];
+    DevBuf<double> d_om, d_ftau;    // nbatch x m
+    // back-substitution
+    DevBuf<double> d_x;
+
+    // results (host)
+    int m = 0, root_ld = 0;
+    std::vector<double> root;       // nbatch x m x root_ld
+    std::vector<double> tau0;       // nbatch x n
+    std::vector<double> final_om, final_tau;   // nbatch x m
+    std::vector<double> rates;      // nbatch x 4
+    std::vector<double> xq;         // nbatch x npos x 2
+    bool have_phase1 = false, have_phase2 = false, have_backsub = false, values_loaded = false;
+
+    ngt_stats st{};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+    ~Engine() {
+        for (auto &e : ev)
+            if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    ngt::LaunchCtx ctx(double *pool, long long stride, const DFront *fr) {
+        ngt::LaunchCtx c;
+        c.pool = pool;
+        c.pool_stride = stride;
+        c.nbatch = nbatch;
+        c.fronts = fr;
+        c.wbuf = d_wbuf.p;
+        c.maxfb = maxfb;
+        c.errflag = d_err.p;
+        c.stream = stream;
+        c.gemm_path = opt.gemm_path;
+        return c;
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    void init_device() {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw CudaError(std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                            " — kmc_rates_b200 has no CPU fallback");
+        device = opt.device;
+        if (device < 0 || device >= ndev) throw InvalidError("device ordinal out of range");
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (auto &x : ev) CK(cudaEventCreate(&x));
+        d_err.alloc(1);
+        CK(cudaMemset(d_err.p, 0, sizeof(int)));
+    }
+
+    void validate_groups() {
+        if (A.empty() || B.empty()) throw InvalidError("A and B must each contain at least one node");
+        std::vector<char> seen(n, 0);
+        for (int64_t a : A) {
+            if (a < 0 || a >= n) throw InvalidError("an element in the reactant set (A) is not in the graph");
+            if (seen[a]) throw InvalidError("duplicate node in A");
+            seen[a] = 1;
+        }
+        for (int64_t b : B) {
+            if (b < 0 || b >= n) throw InvalidError("an element in the product set (B) is not in the graph");
+            if (seen[b] == 1) throw InvalidError("A and B have at least one node in common");
+            if (seen[b] == 2) throw InvalidError("duplicate node in B");
+            seen[b] = 2;
+        }
+    }
+
+    static std::vector<HostBatch> make_batches(const Symbolic &S, std::vector<int> &flat) {
+        std::vector<HostBatch> out;
+        for (const auto &b : S.batches) {
+            HostBatch hb;
+            hb.dev_off = flat.size();
+            for (int id : b.fronts) {
+                hb.ids.push_back(id);
+                hb.f.push_back(S.fronts[id].f);
+                hb.k.push_back(S.fronts[id].k);
+                hb.max_k = std::max(hb.max_k, S.fronts[id].k);
+                flat.push_back(id);
+            }
+            out.push_back(hb);
+        }
+        return out;
+    }
+
+    void upload_structure() {
+        const int nf = (int)S.fronts.size();
+        std::vector<DFront> hf(nf);
+        for (int i = 0; i < nf; ++i) {
+            hf[i].off = S.fronts[i].off;
+            hf[i].f = S.fronts[i].f;
+            hf[i].k = S.fronts[i].k;
+            hf[i].ld = S.fronts[i].ld;
+            hf[i].parent = S.fronts[i].parent;
+        }
+        d_fronts.upload(hf);
+        std::vector<int> flat;
+        batches = make_batches(S, flat);
+        for (auto &b : batches) maxfb = std::max(maxfb, (int)b.ids.size());
+
+        // extend-add rounds: round r of level L = the r-th child of every parent at level L
+        rounds.clear();
+        std::vector<std::vector<std::vector<int> > > per_level(S.n_levels);
+        for (int p = 0; p < nf; ++p) {
+            const int64_t c0 = S.child_ptr[p], c1 = S.child_ptr[p + 1];
+            auto &lv = per_level[S.fronts[p].level];
+            if ((int64_t)lv.size() < c1 - c0) lv.resize(c1 - c0);
+            for (int64_t c = c0; c < c1; ++c) lv[c - c0].push_back(S.child_ids[c]);
+        }
+        for (int l = 0; l < S.n_levels; ++l)
+            for (auto &r : per_level[l]) {
+                // gridDim.y limit: split long rounds
+                for (size_t s0 = 0; s0 < r.size(); s0 += 32768) {
+                    Round rd;
+                    rd.level = l;
+                    rd.dev_off = flat.size();
+                    rd.count = (int)std::min<size_t>(32768, r.size() - s0);
+                    rd.max_m = 0;
+                    for (int i = 0; i < rd.count; ++i) {
+                        rd.max_m = std::max(rd.max_m, S.fronts[r[s0 + i]].m);
+                        flat.push_back(r[s0 + i]);
+                    }
+                    rounds.push_back(rd);
+                }
+            }
+        d_ids.upload(flat);
+        d_rel.upload(S.rel);
+        {
+            std::vector<long long> ro(S.rel_off.begin(), S.rel_off.end());
+            d_rel_off.upload(ro);
+        }
+        d_fidx.upload(S.fidx);
+        {
+            std::vector<long long> io(nf);
+            for (int i = 0; i < nf; ++i) io[i] = S.fronts[i].idx_off;
+            d_idx_off.upload(io);
+        }
+        m = (int)(S.nA + S.nB);
+        root_ld = S.fronts[S.root_id].ld;
+        pool_stride = S.pool_doubles;
+        d_pool.alloc((size_t)pool_stride * nbatch);
+        d_tau0.alloc((size_t)n * nbatch);
+        CK(cudaMemset(d_tau0.p, 0, (size_t)n * nbatch * sizeof(double)));
+
+        build_phase2_structure();
+        d_wbuf.alloc((size_t)nbatch * maxfb * ngt::NB_INNER * ngt::NB_INNER);
+        d_om.alloc((size_t)nbatch * m);
+        d_ftau.alloc((size_t)nbatch * m);
+
+        st.n_nodes = n;
+        st.n_rates = nnz;
+        st.n_eliminated = S.nI;
+        st.n_fronts = nf;
+        st.n_levels = S.n_levels;
+        st.max_front = S.max_front;
+        st.pool_doubles = pool_stride * nbatch;
+        st.alg_flops = S.alg_flops * nbatch;
+        st.alg_bytes = S.alg_bytes * nbatch;
+    }
+
+    // phase-2 task fronts: group g (0 = A, 1 = B), task t -> front of order ng+1 with ng-1 pivots
+    void build_phase2_structure() {
+        std::vector<DFront> pf;
+        std::vector<int> flat;
+        long long off = 0;
+        const int ngs[2] = {(int)S.nA, (int)S.nB};
+        for (int g = 0; g < 2; ++g) {
+            p2batches[g].clear();
+            const int ng = ngs[g];
+            HostBatch hb;
+            for (int t = 0; t < ng; ++t) {
+                DFront F;
+                F.f = ng + 1;
+                F.k = ng - 1;
+                F.ld = ((F.f + 1 + 7) / 8) * 8;
+                F.off = off;
+                F.parent = -1;
+                off += (long long)F.f * F.ld;
+                off = ((off + 15) / 16) * 16;
+                if (hb.ids.size() == 32768) {
+                    p2batches[g].push_back(hb);
+                    hb = HostBatch();
+                }
+                if (hb.ids.empty()) hb.dev_off = flat.size();
+                hb.ids.push_back((int)pf.size());
+                hb.f.push_back(F.f);
+                hb.k.push_back(F.k);
+                hb.max_k = std::max(hb.max_k, F.k);
+                flat.push_back((int)pf.size());
+                pf.push_back(F);
+            }
+            if (!hb.ids.empty()) p2batches[g].push_back(hb);
+            for (auto &b : p2batches[g]) maxfb = std::max(maxfb, (int)b.ids.size());
+        }
+        p2_stride = off;
+        d_p2fronts.upload(pf);
+        d_p2ids.upload(flat);
+        d_p2pool.alloc((size_t)p2_stride * nbatch);
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // blocked elimination of a batch of fronts (panel -> row panel -> Schur updates)
+    // ---------------------------------------------------------------------------------------------
+    static int max_tiles(const HostBatch &b, int j, int mode, int tm, int tn, double &flops) {
+        int mx = 0;
+        ngt::Region R;
+        for (size_t i = 0; i < b.ids.size(); ++i) {
+            if (!ngt::get_region(b.f[i], b.k[i], j, mode, R)) continue;
+            const int t = ((R.r1 - R.r0 + tm - 1) / tm) * ((R.c1 - R.c0 + tn - 1) / tn);
+            mx = std::max(mx, t);
+            flops += 2.0 * (R.r1 - R.r0) * (double)(R.c1 - R.c0) * (R.k1 - R.k0);
+        }
+        return mx;
+    }
+
+    void eliminate(const ngt::LaunchCtx &c, const HostBatch &b, const int *dev_ids) {
+        const int nfb = (int)b.ids.size();
+        const int tm = ngt::update_tile_m(opt.gemm_path), tn = ngt::update_tile_n(opt.gemm_path);
+        const int *ids = dev_ids + b.dev_off;
+        for (int j = 0; j < b.max_k; j += ngt::NB_INNER) {
+            ngt::launch_panel(c, ids, nfb, j);
+            int max_cols = 0;
+            for (int i = 0; i < nfb; ++i)
+                if (b.k[i] > j) max_cols = std::max(max_cols, b.f[i] + 1 - std::min(j + ngt::NB_INNER, b.k[i]));
+            ngt::launch_rowpanel(c, ids, nfb, j, max_cols);
+            st.n_launches += 2;
+            for (int mode = 0; mode < 3; ++mode) {
+                double fl = 0;
+                const int mt = max_tiles(b, j, mode, tm, tn, fl);
+                st.schur_flops += fl * nbatch;
+                if (mt > 0) {
+                    ngt::launch_update(c, ids, nfb, j, mode, mt);
+                    st.n_launches++;
+                }
+            }
+        }
+    }
+
+    void check_errflag(const char *where) {
+        int flag = 0;
+        CK(cudaMemcpyAsync(&flag, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (flag) {
+            CK(cudaMemset(d_err.p, 0, sizeof(int)));
+            if (flag & 2) throw NumericError(std::string(where) + ": a node has no outgoing rate (tau = 1/0)");
+            throw NumericError(std::string(where) +
+                               ": a pivot 1-P_xx was zero or not finite (node cannot reach the rest of the graph)");
+        }
+    }
+
+    void ingest() {
+        CK(cudaMemsetAsync(d_pool.p, 0, (size_t)pool_stride * nbatch * sizeof(double), stream));
+        if (dense) {
+            const int f0 = S.nI > 0 ? 0 : S.root_id;
+            DFront F0, R;
+            auto cv = [&](int id) {
+                DFront d;
+                d.off = S.fronts[id].off; d.f = S.fronts[id].f; d.k = S.fronts[id].k; d.ld = S.fronts[id].ld;
+                d.parent = S.fronts[id].parent;
+                return d;
+            };
+            F0 = cv(f0);
+            R = cv(S.root_id);
+            ngt::launch_ingest_dense(d_pool.p, pool_stride, nbatch, d_K, (int)n, d_pos.p, (int)S.nI, F0, R, d_tau0.p,
+                                     d_err.p, stream);
+        } else {
+            ngt::launch_ingest_sparse(d_pool.p, pool_stride, nbatch, d_k.p, nnz, n_rows, d_row_ptr.p, d_row_node.p,
+                                      d_korig.p, d_dest.p, d_tau_dest.p, d_tau0.p, n, d_err.p, stream);
+        }
+        st.n_launches += 1;
+    }
+
+    void phase_one() {
+        if (!values_loaded) throw StateError("no rate constants loaded");
+        CK(cudaSetDevice(device));
+        st.n_launches = 0;
+        st.schur_flops = 0;
+        CK(cudaEventRecord(ev[0], stream));
+        ingest();
+        CK(cudaEventRecord(ev[1], stream));
+        ngt::LaunchCtx c = ctx(d_pool.p, pool_stride, d_fronts.p);
+        size_t ri = 0, bi = 0;
+        for (int l = 0; l < S.n_levels; ++l) {
+            for (; ri < rounds.size() && rounds[ri].level == l; ++ri) {
+                ngt::launch_extend_add(c, d_ids.p + rounds[ri].dev_off, rounds[ri].count, rounds[ri].max_m, d_rel.p,
+                                       d_rel_off.p);
+                st.n_launches++;
+            }
+            for (; bi < batches.size() && S.batches[bi].level == l; ++bi) eliminate(c, batches[bi], d_ids.p);
+        }
+        CK(cudaEventRecord(ev[2], stream));
+        have_phase1 = true;
+        have_phase2 = false;
+        have_backsub = false;
+    }
+
+    void download_root() {
+        const DFront R{S.fronts[S.root_id].off, S.fronts[S.root_id].f, 0, S.fronts[S.root_id].ld, -1};
+        root.resize((size_t)nbatch * m * root_ld);
+        const size_t blk = (size_t)m * root_ld;
+        if (nbatch <= 8) {   // (a 2-D copy's pitch is limited to 2 GiB; single networks can exceed it)
+            for (int b = 0; b < nbatch; ++b)
+                CK(cudaMemcpyAsync(root.data() + b * blk, d_pool.p + (size_t)b * pool_stride + R.off,
+                                   blk * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        } else {
+            CK(cudaMemcpy2DAsync(root.data(), blk * sizeof(double), d_pool.p + R.off,
+                                 (size_t)pool_stride * sizeof(double), blk * sizeof(double), nbatch,
+                                 cudaMemcpyDeviceToHost, stream));
+        }
+        tau0.resize((size_t)nbatch * n);
+        CK(cudaMemcpyAsync(tau0.data(), d_tau0.p, tau0.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
+
+    void phase_two(int rank = 0, int nranks = 1) {
+        if (!have_phase1) throw StateError("phase_two called before phase_one");
+        CK(cudaSetDevice(device));
+        CK(cudaEventRecord(ev[3], stream));
+        const DFront R{S.fronts[S.root_id].off, S.fronts[S.root_id].f, 0, S.fronts[S.root_id].ld, -1};
+        ngt::LaunchCtx c1 = ctx(d_pool.p, pool_stride, d_fronts.p);
+        ngt::LaunchCtx c2 = ctx(d_p2pool.p, p2_stride, d_p2fronts.p);
+        const int nA = (int)S.nA, nB = (int)S.nB;
+        CK(cudaMemsetAsync(d_p2pool.p, 0, (size_t)p2_stride * nbatch * sizeof(double), stream));
+        for (int g = 0; g < 2; ++g) {
+            const int ng = g == 0 ? nA : nB, g0 = g == 0 ? 0 : nA, o0 = g == 0 ? nA : 0, no = g == 0 ? nB : nA;
+            const int task0 = g == 0 ? 0 : nA;
+            ngt::launch_phase2_gather(c1, R, g0, ng, o0, no, d_p2pool.p, p2_stride, d_p2fronts.p, task0, ng, rank, nranks);
+            st.n_launches++;
+            // sharded run: fronts of other ranks stay zero; their pivots would be 0/0, so eliminate only owned tasks
+            if (nranks > 1) {
+                for (const auto &b : p2batches[g]) {
+                    HostBatch mine;
+                    mine.dev_off = 0;
+                    std::vector<int> ids;
+                    for (size_t i = 0; i < b.ids.size(); ++i)
+                        if (((b.ids[i] - task0) % nranks) == rank) {
+                            mine.ids.push_back(b.ids[i]); mine.f.push_back(b.f[i]); mine.k.push_back(b.k[i]);
+                            mine.max_k = std::max(mine.max_k, b.k[i]);
+                        }
+                    if (mine.ids.empty()) continue;
+                    shard_ids.emplace_back();
+                    shard_ids.back().upload(mine.ids);
+                    eliminate(c2, mine, shard_ids.back().p);
+                }
+            } else {
+                for (const auto &b : p2batches[g]) eliminate(c2, b, d_p2ids.p);
+            }
+            ngt::launch_phase2_collect(c2, d_p2pool.p, p2_stride, d_p2fronts.p, task0, ng, ng, d_om.p, d_ftau.p, m, g0,
+                                       rank, nranks);
+            st.n_launches++;
+        }
+        CK(cudaEventRecord(ev[4], stream));
+        final_om.resize((size_t)nbatch * m);
+        final_tau.resize((size_t)nbatch * m);
+        CK(cudaMemcpyAsync(final_om.data(), d_om.p, final_om.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(final_tau.data(), d_ftau.p, final_tau.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        download_root();
+        check_errflag("phase two");
+        shard_ids.clear();
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev[0], ev[1]); st.ms_ingest = ms;
+        cudaEventElapsedTime(&ms, ev[1], ev[2]); st.ms_phase1 = ms;
+        cudaEventElapsedTime(&ms, ev[3], ev[4]); st.ms_phase2 = ms;
+        have_phase2 = true;
+        if (nranks == 1) finish_rates();
+    }
+    std::vector<DevBuf<int> > shard_ids;
+
+    // reference ngt.hpp:444-513
+    void finish_rates() {
+        rates.assign((size_t)nbatch * 4, 0.0);
+        const int nA = (int)S.nA, nB = (int)S.nB;
+        for (int b = 0; b < nbatch; ++b) {
+            const double *R = root.data() + (size_t)b * m * root_ld;
+            const double *om = final_om.data() + (size_t)b * m, *ft = final_tau.data() + (size_t)b * m;
+            const double *t0 = tau0.data() + (size_t)b * n;
+            for (int g = 0; g < 2; ++g) {
+                const int g0 = g == 0 ? 0 : nA, ng = g == 0 ? nA : nB, o0 = g == 0 ? nA : 0, no = g == 0 ? nB : nA;
+                const std::vector<int64_t> &grp = g == 0 ? A : B;
+                double s = 0, ss = 0, norm = 0;
+                for (int i = 0; i < ng; ++i) {
+                    const double w = have_weights ? weights[grp[i]] : 1.0;
+                    s += w * om[g0 + i] / ft[g0 + i];
+                    double PaB = 0;
+                    for (int c = 0; c < no; ++c) PaB += R[(size_t)(g0 + i) * root_ld + o0 + c];
+                    ss += w * PaB / t0[grp[i]];
+                    norm += w;
+                }
+                rates[(size_t)b * 4 + g] = s / norm;
+                rates[(size_t)b * 4 + 2 + g] = ss / norm;
+            }
+        }
+    }
+
+    // committors and MFPTs of every eliminated node by back-substitution (top-down over the assembly tree)
+    void backsub() {
+        if (!have_phase1) throw StateError("committors requested before phase one");
+        CK(cudaSetDevice(device));
+        const int64_t npos = S.nI + S.nA + S.nB;
+        std::vector<double> x0((size_t)npos * 2, 0.0);
+        for (int64_t i = 0; i < S.nB; ++i) x0[(size_t)(S.nI + S.nA + i) * 2] = 1.0;
+        d_x.alloc((size_t)nbatch * npos * 2);
+        for (int b = 0; b < nbatch; ++b)
+            CK(cudaMemcpyAsync(d_x.p + (size_t)b * npos * 2, x0.data(), x0.size() * sizeof(double),
+                               cudaMemcpyHostToDevice, stream));
+        ngt::LaunchCtx c = ctx(d_pool.p, pool_stride, d_fronts.p);
+        for (size_t bi = batches.size(); bi-- > 0;) {
+            const HostBatch &b = batches[bi];
+            const int last = ((b.max_k - 1) / ngt::NB_INNER) * ngt::NB_INNER;
+            for (int j = last; j >= 0; j -= ngt::NB_INNER) {
+                ngt::launch_backsub_step(c, d_ids.p + b.dev_off, (int)b.ids.size(), d_fidx.p, d_idx_off.p, d_x.p,
+                                         npos * 2, j);
+                st.n_launches++;
+            }
+        }
+        xq.resize((size_t)nbatch * npos * 2);
+        CK(cudaMemcpyAsync(xq.data(), d_x.p, xq.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        have_backsub = true;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// construction helpers
+// ---------------------------------------------------------------------------------------------------
+Engine *make_engine(const ngt_options *opt, int64_t nbatch) {
+    Engine *E = new Engine();
+    if (opt) E->opt = *opt;
+    if (nbatch < 1) { delete E; throw InvalidError("nbatch must be >= 1"); }
+    E->nbatch = (int)nbatch;
+    return E;
+}
+
+void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, const double *k,
+                  int64_t nA, const int64_t *A, int64_t nB, const int64_t *B) {
+    auto t0 = std::chrono::steady_clock::now();
+    if (n <= 0 || nnz < 0) throw InvalidError("empty network");
+    if (n > 2000000000LL) throw InvalidError("too many nodes");
+    E->n = n;
+    E->nnz = nnz;
+    E->dense = false;
+    E->A.assign(A, A + nA);
+    E->B.assign(B, B + nB);
+    E->validate_groups();
+    std::vector<char> present(n, 0);
+    std::vector<int64_t> outdeg(n + 1, 0);
+    for (int64_t e = 0; e < nnz; ++e) {
+        if (src[e] < 0 || src[e] >= n || dst[e] < 0 || dst[e] >= n) throw InvalidError("rate endpoint out of range");
+        present[src[e]] = present[dst[e]] = 1;
+        outdeg[src[e] + 1]++;
+    }
+    for (int64_t a : E->A) if (!present[a]) throw InvalidError("an element in the reactant set (A) is not in the graph");
+    for (int64_t b : E->B) if (!present[b]) throw InvalidError("an element in the product set (B) is not in the graph");
+    for (int64_t u = 0; u < n; ++u)
+        if (present[u] && outdeg[u + 1] == 0) throw InvalidError("node " + std::to_string(u) + " has no outgoing rate");
+
+    ngt::Adjacency g;
+    ngt::build_adjacency(n, nnz, src, dst, g);
+    ngt::analyse_sparse(g, present, E->A, E->B, E->opt.leaf_size, E->S);
+    const Symbolic &S = E->S;
+
+    // CSR by source over present nodes, (src,dst) duplicates resolved "last wins" (std::map semantics, ngt.pyx:76-81)
+    for (int64_t u = 0; u < n; ++u) outdeg[u + 1] += outdeg[u];
+    std::vector<int64_t> fill(outdeg.begin(), outdeg.end() - 1);
+    std::vector<int32_t> ent(nnz);
+    for (int64_t e = 0; e < nnz; ++e) ent[fill[src[e]]++] = (int32_t)e;   // stable: increasing e inside a row
+    std::vector<long long> row_ptr;
+    std::vector<int> row_node, korig;
+    std::vector<long long> dest, tau_dest;
+    row_ptr.push_back(0);
+    std::vector<int32_t> rowbuf;
+    for (int64_t u = 0; u < n; ++u) {
+        if (!present[u]) continue;
+        rowbuf.assign(ent.begin() + outdeg[u], ent.begin() + outdeg[u + 1]);
+        std::stable_sort(rowbuf.begin(), rowbuf.end(), [&](int32_t a, int32_t b) { return dst[a] < dst[b]; });
+        const int32_t pu = S.pos[u];
+        for (size_t i = 0; i < rowbuf.size(); ++i) {
+            if (i + 1 < rowbuf.size() && dst[rowbuf[i + 1]] == dst[rowbuf[i]]) continue;   // keep the last duplicate
+            const int32_t e = rowbuf[i];
+            const int32_t pv = S.pos[dst[e]];
+            const int32_t owner = S.pos_front[std::min(pu, pv)];
+            const ngt::Front &F = S.fronts[owner];
+            const int32_t lr = ngt::local_index(S, owner, pu), lc = ngt::local_index(S, owner, pv);
+            if (lr < 0 || lc < 0) throw std::logic_error("ingest: entry has no slot in its front");
+            korig.push_back(e);
+            dest.push_back(F.off + (long long)lr * F.ld + lc);
+        }
+        row_ptr.push_back((long long)korig.size());
+        row_node.push_back((int)u);
+        const int32_t owner = S.pos_front[pu];
+        const ngt::Front &F = S.fronts[owner];
+        const int32_t lr = ngt::local_index(S, owner, pu);
+        tau_dest.push_back(F.off + (long long)lr * F.ld + F.f);
+    }
+    E->n_rows = (int)row_node.size();
+    E->init_device();
+    E->d_row_ptr.upload(row_ptr);
+    E->d_row_node.upload(row_node);
+    E->d_korig.upload(korig);
+    E->d_dest.upload(dest);
+    E->d_tau_dest.upload(tau_dest);
+    E->upload_structure();
+    E->d_k.alloc((size_t)nnz * E->nbatch);
+    if (k) {
+        CK(cudaMemcpy(E->d_k.p, k, (size_t)nnz * E->nbatch * sizeof(double), cudaMemcpyHostToDevice));
+        E->values_loaded = true;
+    }
+    E->st.ms_symbolic = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+void build_dense(Engine *E, int64_t n, const double *K, bool on_device, int64_t nA, const int64_t *A, int64_t nB,
+                 const int64_t *B) {
+    auto t0 = std::chrono::steady_clock::now();
+    if (n <= 1) throw InvalidError("empty network");
+    if (n > 1000000) throw InvalidError("dense network too large");
+    E->n = n;
+    E->nnz = n * n;
+    E->dense = true;
+    E->A.assign(A, A + nA);
+    E->B.assign(B, B + nB);
+    E->validate_groups();
+    ngt::analyse_dense(n, E->A, E->B, E->S);
+    E->init_device();
+    E->d_pos.upload(E->S.pos);
+    E->upload_structure();
+    if (K) {
+        if (on_device) {
+            E->d_K = K;
+        } else {
+            E->d_K_owned.alloc((size_t)n * n * E->nbatch);
+            CK(cudaMemcpy(E->d_K_owned.p, K, (size_t)n * n * E->nbatch * sizeof(double), cudaMemcpyHostToDevice));
+            E->d_K = E->d_K_owned.p;
+        }
+        E->values_loaded = true;
+    }
+    E->st.ms_symbolic = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+template <class Fn>
+int guard(Fn &&fn) {
+    try {
+        fn();
+        return NGT_OK;
+    } catch (const InvalidError &e) {
+        g_err = e.what();
+        return NGT_E_INVALID;
+    } catch (const CudaError &e) {
+        g_err = e.what();
+        return NGT_E_CUDA;
+    } catch (const StateError &e) {
+        g_err = e.what();
+        return NGT_E_STATE;
+    } catch (const NumericError &e) {
+        g_err = e.what();
+        return NGT_E_NUMERIC;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return NGT_E_INVALID;
+    }
+}
+
+Engine *eng(ngt_handle h) {
+    if (!h) throw InvalidError("null handle");
+    return reinterpret_cast<Engine *>(h);
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char *ngt_last_error(void) { return g_err.c_str(); }
+const char *ngt_version(void) { return "kmc_rates_b200 0.1 (sm_100a)"; }
+
+int ngt_batch_create(int64_t nbatch, int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, const double *k,
+                     int64_t nA, const int64_t *A, int64_t nB, const int64_t *B, const ngt_options *opt,
+                     ngt_handle *out) {
+    return guard([&] {
+        if (!out) throw InvalidError("null output handle");
+        *out = nullptr;
+        if (!src || !dst || !A || !B) throw InvalidError("null input pointer");
+        Engine *E = make_engine(opt, nbatch);
+        try {
+            build_sparse(E, n, nnz, src, dst, k, nA, A, nB, B);
+        } catch (...) {
+            delete E;
+            throw;
+        }
+        *out = reinterpret_cast<ngt_handle>(E);
+    });
+}
+
+int ngt_create(int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, const double *k, int64_t nA,
+               const int64_t *A, int64_t nB, const int64_t *B, const ngt_options *opt, ngt_handle *out) {
+    return ngt_batch_create(1, n, nnz, src, dst, k, nA, A, nB, B, opt, out);
+}
+
+static int create_dense_any(int64_t nbatch, int64_t n, const double *K, bool dev, int64_t nA, const int64_t *A,
+                            int64_t nB, const int64_t *B, const ngt_options *opt, ngt_handle *out) {
+    return guard([&] {
+        if (!out) throw InvalidError("null output handle");
+        *out = nullptr;
+        if (!A || !B) throw InvalidError("null input pointer");
+        Engine *E = make_engine(opt, nbatch);
+        try {
+            build_dense(E, n, K, dev, nA, A, nB, B);
+        } catch (...) {
+            delete E;
+            throw;
+        }
+        *out = reinterpret_cast<ngt_handle>(E);
+    });
+}
+
+int ngt_create_dense(int64_t n, const double *K, int64_t nA, const int64_t *A, int64_t nB, const int64_t *B,
+                     const ngt_options *opt, ngt_handle *out) {
+    return create_dense_any(1, n, K, false, nA, A, nB, B, opt, out);
+}
+int ngt_create_dense_dev(int64_t n, const double *K, int64_t nA, const int64_t *A, int64_t nB, const int64_t *B,
+                         const ngt_options *opt, ngt_handle *out) {
+    return create_dense_any(1, n, K, true, nA, A, nB, B, opt, out);
+}
+int ngt_batch_create_dense(int64_t nbatch, int64_t n, const double *K, int64_t nA, const int64_t *A, int64_t nB,
+                           const int64_t *B, const ngt_options *opt, ngt_handle *out) {
+    return create_dense_any(nbatch, n, K, false, nA, A, nB, B, opt, out);
+}
+int ngt_batch_create_dense_dev(int64_t nbatch, int64_t n, const double *K, int64_t nA, const int64_t *A, int64_t nB,
+                               const int64_t *B, const ngt_options *opt, ngt_handle *out) {
+    return create_dense_any(nbatch, n, K, true, nA, A, nB, B, opt, out);
+}
+
+static int set_rates_any(ngt_handle h, const double *k, bool dev) {
+    return guard([&] {
+        Engine *E = eng(h);
+        if (!k) throw InvalidError("null rate pointer");
+        CK(cudaSetDevice(E->device));
+        const size_t cnt = (size_t)E->nnz * E->nbatch;
+        if (E->dense) {
+            if (dev) {
+                E->d_K = k;
+            } else {
+                if (!E->d_K_owned.p) E->d_K_owned.alloc(cnt);
+                CK(cudaMemcpy(E->d_K_owned.p, k, cnt * sizeof(double), cudaMemcpyHostToDevice));
+                E->d_K = E->d_K_owned.p;
+            }
+        } else {
+            CK(cudaMemcpy(E->d_k.p, k, cnt * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+        }
+        E->values_loaded = true;
+        E->have_phase1 = E->have_phase2 = E->have_backsub = false;
+    });
+}
+int ngt_set_rates(ngt_handle h, const double *k) { return set_rates_any(h, k, false); }
+int ngt_set_rates_dev(ngt_handle h, const double *k) { return set_rates_any(h, k, true); }
+
+int ngt_set_weights(ngt_handle h, int64_t nw, const int64_t *ids, const double *w) {
+    return guard([&] {
+        Engine *E = eng(h);
+        if (nw > 0 && (!ids || !w)) throw InvalidError("null weight pointer");
+        if (!E->have_weights) E->weights.assign(E->n, 1.0);
+        E->have_weights = true;
+        for (int64_t i = 0; i < nw; ++i)
+            if (ids[i] >= 0 && ids[i] < E->n) E->weights[ids[i]] = w[i];   // unknown ids ignored, as ngt.pyx:99-103
+        if (E->have_phase2) E->finish_rates();
+    });
+}
+
+void ngt_destroy(ngt_handle h) {
+    if (!h) return;
+    Engine *E = reinterpret_cast<Engine *>(h);
+    cudaSetDevice(E->device);
+    delete E;
+}
+
+int ngt_phase_one(ngt_handle h) {
+    return guard([&] {
+        Engine *E = eng(h);
+        E->phase_one();
+        CK(cudaStreamSynchronize(E->stream));
+        E->check_errflag("phase one");
+        float ms = 0;
+        cudaEventElapsedTime(&ms, E->ev[0], E->ev[1]); E->st.ms_ingest = ms;
+        cudaEventElapsedTime(&ms, E->ev[1], E->ev[2]); E->st.ms_phase1 = ms;
+    });
+}
+
+int ngt_phase_two(ngt_handle h) {
+    return guard([&] { eng(h)->phase_two(); });
+}
+
+int ngt_phase_two_shard(ngt_handle h, int32_t rank, int32_t nranks) {
+    return guard([&] {
+        if (nranks < 1 || rank < 0 || rank >= nranks) throw InvalidError("bad rank / nranks");
+        eng(h)->phase_two(rank, nranks);
+    });
+}
+
+int ngt_compute_rates(ngt_handle h) {
+    return guard([&] {
+        Engine *E = eng(h);
+        E->phase_one();
+        E->phase_two();
+    });
+}
+
+int ngt_compute_rates_and_committors(ngt_handle h) {
+    return guard([&] {
+        Engine *E = eng(h);
+        E->phase_one();
+        E->phase_two();
+        E->backsub();
+    });
+}
+
+int ngt_get_rates(ngt_handle h, double out4[4]) {
+    return guard([&] {
+        Engine *E = eng(h);
+        if (!E->have_phase2 || E->rates.empty()) throw StateError("compute_rates has not been called");
+        for (int i = 0; i < 4; ++i) out4[i] = E->rates[i];
+    });
+}
+
+int ngt_batch_get_rates(ngt_handle h, double *out) {
+    return guard([&] {
+        Engine *E = eng(h);
+        if (!E->have_phase2 || E->rates.empty()) throw StateError("compute_rates has not been called");
+        std::memcpy(out, E->rates.data(), E->rates.size() * sizeof(double));
+    });
+}
+
+int ngt_get_final(ngt_handle h, double *omPxx, double *tau) {
+    return guard([&] {
+        Engine *E = eng(h);
+        if (!E->have_phase2) throw StateError("compute_rates has not been called");
+        std::memcpy(omPxx, E->final_om.data(), (size_t)E->m * sizeof(double));
+        std::memcpy(tau, E->final_tau.data(), (size_t)E->m * sizeof(double));
+    });
+}
+
+int ngt_set_final(ngt_handle h, const double *omPxx, const double *tau) {
+    return guard([&] {
+        Engine *E = eng(h);
+        if (!E->have_phase2) throw StateError("phase two has not been run");
+        std::memcpy(E->final_om.data(), omPxx, (size_t)E->m * E->nbatch * sizeof(double));
+        std::memcpy(E->final_tau.data(), tau, (size_t)E->m * E->nbatch * sizeof(double));
+        E->finish_rates();
+    });
+}
+
+int ngt_get_reduced(ngt_handle h, double *P, double *tau) {
+    return guard([&] {
+        Engine *E = eng(h);
+        if (!E->have_phase1) throw StateError("phase one has not been run");
+        if (!E->have_phase2) {
+            E->download_root();
+            CK(cudaStreamSynchronize(E->stream));
+        }
+        for (int i = 0; i < E->m; ++i) {
+            for (int j = 0; j < E->m; ++j) P[(size_t)i * E->m + j] = E->root[(size_t)i * E->root_ld + j];
+            tau[i] = E->root[(size_t)i * E->root_ld + E->m];
+        }
+    });
+}
+
+int ngt_get_initial_tau(ngt_handle h, double *tau) {
+    return guard([&] {
+        Engine *E = eng(h);
+        if (!E->have_phase1) throw StateError("phase one has not been run");
+        if (E->tau0.empty()) {
+            E->download_root();
+            CK(cudaStreamSynchronize(E->stream));
+        }
+        std::memcpy(tau, E->tau0.data(), (size_t)E->n * sizeof(double));
+    });
+}
+
+static int get_x(ngt_handle h, double *out, int which) {
+    return guard([&] {
+        Engine *E = eng(h);
+        if (!E->have_backsub) E->backsub();
+        const double nan = std::nan("");
+        for (int64_t u = 0; u < E->n; ++u) {
+            const int32_t p = E->S.pos[u];
+            out[u] = p < 0 ? nan : E->xq[(size_t)p * 2 + which];
+        }
+    });
+}
+int ngt_get_committors(ngt_handle h, double *q) { return get_x(h, q, 0); }
+int ngt_get_mfpt(ngt_handle h, double *t) { return get_x(h, t, 1); }
+
+int ngt_get_stats(ngt_handle h, ngt_stats *st) {
+    return guard([&] {
+        Engine *E = eng(h);
+        *st = E->st;
+    });
+}
+
+int ngt_reduced_block_dev(ngt_handle h, double **dptr, int64_t *ndoubles) {
+    return guard([&] {
+        Engine *E = eng(h);
+        *dptr = E->d_pool.p + E->S.fronts[E->S.root_id].off;
+        *ndoubles = (int64_t)E->m * E->root_ld;
+    });
+}
+
+}  // extern "C"

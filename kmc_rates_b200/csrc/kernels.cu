@@ -1,0 +1,525 @@
+// CUDA kernels of the multifrontal NGT engine, written for sm_100a (B200).
+// Layout and the blocked elimination scheme are described in kernels.cuh.
+#include "kernels.cuh"
+
+#include <cstdio>
+
+namespace ngt {
+
+// =====================================================================================================
+// helpers
+// =====================================================================================================
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// =====================================================================================================
+// panel kernel: one CTA (1024 threads, thread (u,q)) per front and network.
+//   s_u  = sum_{v >= je} P[j+u, v]                (mass leaving the panel; GTH row sums)
+//   W    = (I - P_XX)^-1 by subtraction-free Gauss-Jordan; pivot d_p = sum_{q != p} T[p,q] + s_p
+// =====================================================================================================
+__global__ void __launch_bounds__(1024, 1)
+panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j,
+             double *wbuf, int maxfb, int *errflag) {
+    const DFront F = fronts[ids[blockIdx.x]];
+    if (j >= F.k) return;
+    double *M = pool + (long long)blockIdx.y * pool_stride + F.off;
+    const int nbp = min(NB_INNER, F.k - j);
+    const int je = j + nbp;
+    const int u = threadIdx.x >> 5, q = threadIdx.x & 31;
+
+    __shared__ double Ts[NB_INNER][NB_INNER + 1];
+    __shared__ double Gs[NB_INNER][NB_INNER + 1];
+    __shared__ double Ss[NB_INNER];
+    __shared__ double Ds[NB_INNER];
+
+    // row sums over everything to the right of the panel (tau column excluded)
+    double s = 0.0;
+    if (u < nbp) {
+        const double *row = M + (long long)(j + u) * F.ld;
+        for (int c = je + q; c < F.f; c += 32) s += row[c];
+        s = warp_sum(s);
+    } else {
+        s = 1.0;   // padding rows behave like isolated absorbing nodes
+    }
+    if (q == 0) Ss[u] = s;
+    Ts[u][q] = (u < nbp && q < nbp && u != q) ? M[(long long)(j + u) * F.ld + j + q] : 0.0;
+    Gs[u][q] = (u == q) ? 1.0 : 0.0;
+
+    for (int p = 0; p < nbp; ++p) {
+        __syncthreads();
+        const double tp = Ts[p][q];
+        const double gp = Gs[p][q];
+        const double sp = Ss[p];
+        const double d = warp_sum(tp) + sp;
+        if (u == p) {
+            if (q == 0) {
+                Ds[p] = d;
+                if (!(d > 0.0) || isinf(d)) atomicOr(errflag, 1);
+            }
+        } else {
+            const double fup = Ts[u][p] / d;
+            __syncwarp();
+            double t = Ts[u][q] + fup * tp;
+            if (q == p || q == u) t = 0.0;
+            Ts[u][q] = t;
+            Gs[u][q] += fup * gp;
+            if (q == 0) Ss[u] = Ss[u] + fup * sp;
+        }
+    }
+    __syncthreads();
+    double *W = wbuf + ((long long)blockIdx.y * maxfb + blockIdx.x) * (NB_INNER * NB_INNER);
+    W[u * NB_INNER + q] = Gs[u][q] / Ds[u < nbp ? u : 0] * (u < nbp ? 1.0 : 0.0);
+}
+
+void launch_panel(const LaunchCtx &c, const int *ids, int nfb, int j) {
+    dim3 grid(nfb, c.nbatch);
+    panel_kernel<<<grid, 1024, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.maxfb, c.errflag);
+}
+
+// =====================================================================================================
+// row panel: U' = W [P_XR | tau_X] in place, columns je..f (f = tau column)
+// 256 threads handle 128 columns: thread (h = tid/128, col = tid%128) produces rows 16h..16h+15
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+rowpanel_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j,
+                const double *wbuf, int maxfb) {
+    const DFront F = fronts[ids[blockIdx.y]];
+    if (j >= F.k) return;
+    const int nbp = min(NB_INNER, F.k - j);
+    const int je = j + nbp;
+    const int col = je + blockIdx.x * 128 + (threadIdx.x & 127);
+    if (je + (int)blockIdx.x * 128 > F.f) return;
+    double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
+
+    __shared__ double Ws[NB_INNER][NB_INNER];
+    const double *W = wbuf + ((long long)blockIdx.z * maxfb + blockIdx.y) * (NB_INNER * NB_INNER);
+    for (int i = threadIdx.x; i < NB_INNER * NB_INNER; i += 256) Ws[i / NB_INNER][i % NB_INNER] = W[i];
+
+    double x[NB_INNER];
+    const bool live = col <= F.f;
+#pragma unroll
+    for (int r = 0; r < NB_INNER; ++r) x[r] = (live && r < nbp) ? M[(long long)(j + r) * F.ld + col] : 0.0;
+    __syncthreads();
+    const int h = threadIdx.x >> 7;
+    if (live) {
+#pragma unroll 4
+        for (int rr = 0; rr < 16; ++rr) {
+            const int r = h * 16 + rr;
+            if (r >= nbp) break;
+            double acc = 0.0;
+#pragma unroll
+            for (int t = 0; t < NB_INNER; ++t) acc += Ws[r][t] * x[t];
+            M[(long long)(j + r) * F.ld + col] = acc;
+        }
+    }
+}
+
+void launch_rowpanel(const LaunchCtx &c, const int *ids, int nfb, int j, int max_cols) {
+    dim3 grid((max_cols + 127) / 128, nfb, c.nbatch);
+    if (grid.x == 0) grid.x = 1;
+    rowpanel_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.maxfb);
+}
+
+// =====================================================================================================
+// Schur update, scalar DFMA path (debug / cross-check): C[r,c] += sum_p F[r,p] F[p,c]
+// 64 x 64 tile, 256 threads, 4 x 4 per thread
+// =====================================================================================================
+constexpr int FT = 64, FK = 16;
+
+__global__ void __launch_bounds__(256)
+update_dfma_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode) {
+    const DFront F = fronts[ids[blockIdx.y]];
+    Region R;
+    if (!get_region(F.f, F.k, j, mode, R)) return;
+    const int tiles_c = (R.c1 - R.c0 + FT - 1) / FT;
+    const int tiles_r = (R.r1 - R.r0 + FT - 1) / FT;
+    const int tr = blockIdx.x / tiles_c, tc = blockIdx.x % tiles_c;
+    if (tr >= tiles_r) return;
+    double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
+    const int rb = R.r0 + tr * FT, cb = R.c0 + tc * FT;
+
+    __shared__ double As[FT][FK + 1];
+    __shared__ double Bs[FK][FT + 1];
+    const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+
+    for (int kb = R.k0; kb < R.k1; kb += FK) {
+        for (int i = threadIdx.x; i < FT * FK; i += 256) {
+            const int r = i / FK, kk = i % FK;
+            As[r][kk] = (rb + r < R.r1 && kb + kk < R.k1) ? M[(long long)(rb + r) * F.ld + kb + kk] : 0.0;
+        }
+        for (int i = threadIdx.x; i < FK * FT; i += 256) {
+            const int kk = i / FT, cc = i % FT;
+            Bs[kk][cc] = (cb + cc < R.c1 && kb + kk < R.k1) ? M[(long long)(kb + kk) * F.ld + cb + cc] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < FK; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[ty * 4 + i][kk]; b[i] = Bs[kk][tx + 16 * i]; }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] += a[x] * b[y];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        const int r = rb + ty * 4 + x;
+        if (r >= R.r1) continue;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int cidx = cb + tx + 16 * y;
+            if (cidx < R.c1) M[(long long)r * F.ld + cidx] += acc[x][y];
+        }
+    }
+}
+
+// =====================================================================================================
+// Schur update on the FP64 tensor cores: DMMA m8n8k4 (the sm_100a FP64 tensor instruction; tcgen05 has
+// no f64 kind).  CTA tile 128 x 64, 8 warps as 4 (M) x 2 (N), warp tile 32 x 32 = 4 x 4 MMA tiles,
+// K staged through shared memory 32 at a time.  Shared strides 36 / 68 doubles make both fragment loads
+// bank-conflict free (stride = 4 mod 16).
+// =====================================================================================================
+constexpr int TM = 128, TN = 64, TK = 32;
+constexpr int AS_LD = TK + 4, BS_LD = TN + 4;
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 2)
+update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode) {
+    const DFront F = fronts[ids[blockIdx.y]];
+    Region R;
+    if (!get_region(F.f, F.k, j, mode, R)) return;
+    const int tiles_c = (R.c1 - R.c0 + TN - 1) / TN;
+    const int tiles_r = (R.r1 - R.r0 + TM - 1) / TM;
+    const int tr = blockIdx.x / tiles_c, tc = blockIdx.x % tiles_c;
+    if (tr >= tiles_r) return;
+    double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
+    const int rb = R.r0 + tr * TM, cb = R.c0 + tc * TN;
+
+    extern __shared__ double smem[];
+    double *As = smem;                    // [TM][AS_LD]
+    double *Bs = smem + TM * AS_LD;       // [TK][BS_LD]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int g = lane >> 2, t4 = lane & 3;
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    for (int kb = R.k0; kb < R.k1; kb += TK) {
+        // A tile: rows rb.., pivots kb..kb+31  (256-byte runs per row)
+#pragma unroll 4
+        for (int i = threadIdx.x; i < TM * TK; i += 256) {
+            const int r = i >> 5, kk = i & 31;
+            As[r * AS_LD + kk] = (rb + r < R.r1 && kb + kk < R.k1) ? M[(long long)(rb + r) * F.ld + kb + kk] : 0.0;
+        }
+        // B tile: pivots kb.., cols cb..cb+63
+#pragma unroll 4
+        for (int i = threadIdx.x; i < TK * TN; i += 256) {
+            const int kk = i >> 6, cc = i & 63;
+            Bs[kk * BS_LD + cc] = (cb + cc < R.c1 && kb + kk < R.k1) ? M[(long long)(kb + kk) * F.ld + cb + cc] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k4 = 0; k4 < TK / 4; ++k4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = As[(wm * 32 + mi * 8 + g) * AS_LD + k4 * 4 + t4];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(k4 * 4 + t4) * BS_LD + wn * 32 + ni * 8 + g];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+        __syncthreads();
+    }
+    // epilogue: C += acc.  Thread holds C[g][2*t4 + {0,1}] of every 8 x 8 tile.
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        const int r = rb + wm * 32 + mi * 8 + g;
+        if (r >= R.r1) continue;
+        double *row = M + (long long)r * F.ld;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
+            if (c0 < R.c1) row[c0] += acc[mi][ni][0];
+            if (c0 + 1 < R.c1) row[c0 + 1] += acc[mi][ni][1];
+        }
+    }
+}
+
+int update_tile_m(int gemm_path) { return gemm_path == 1 ? FT : TM; }
+int update_tile_n(int gemm_path) { return gemm_path == 1 ? FT : TN; }
+
+void launch_update(const LaunchCtx &c, const int *ids, int nfb, int j, int mode, int max_tiles) {
+    if (max_tiles <= 0) return;
+    dim3 grid(max_tiles, nfb, c.nbatch);
+    if (c.gemm_path == 1) {
+        update_dfma_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode);
+    } else {
+        static bool attr_set = false;
+        const size_t smem = (size_t)(TM * AS_LD + TK * BS_LD) * sizeof(double);
+        if (!attr_set) {
+            cudaFuncSetAttribute(update_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        update_dmma_kernel<<<grid, 256, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode);
+    }
+}
+
+// =====================================================================================================
+// ingest
+// =====================================================================================================
+// sparse: one warp per source node.  tau_u = 1 / sum_v k_uv; P_uv = k_uv tau_u scattered to its front slot.
+__global__ void __launch_bounds__(256)
+ingest_sparse_kernel(double *pool, long long pool_stride, const double *k, long long k_stride, int n_rows,
+                     const long long *row_ptr, const int *row_node, const int *korig, const long long *dest,
+                     const long long *tau_dest, double *tau0, long long tau0_stride, int *errflag) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const long long b = blockIdx.y;
+    const double *kb = k + b * k_stride;
+    double *P = pool + b * pool_stride;
+    const long long e0 = row_ptr[row], e1 = row_ptr[row + 1];
+    double s = 0.0;
+    for (long long e = e0 + lane; e < e1; e += 32) s += kb[korig[e]];
+    s = warp_sum(s);
+    const double tau = 1.0 / s;
+    if (lane == 0) {
+        if (!(s > 0.0) || isinf(tau)) atomicOr(errflag, 2);
+        const int u = row_node[row];
+        tau0[b * tau0_stride + u] = tau;
+        if (tau_dest[row] >= 0) P[tau_dest[row]] = tau;
+    }
+    for (long long e = e0 + lane; e < e1; e += 32)
+        if (dest[e] >= 0) P[dest[e]] = kb[korig[e]] * tau;
+}
+
+void launch_ingest_sparse(double *pool, long long pool_stride, int nbatch, const double *k, long long k_stride,
+                          int n_rows, const long long *row_ptr, const int *row_node, const int *korig,
+                          const long long *dest, const long long *tau_dest, double *tau0, long long tau0_stride,
+                          int *errflag, cudaStream_t s) {
+    if (n_rows <= 0) return;
+    dim3 grid((n_rows + 7) / 8, nbatch);
+    ingest_sparse_kernel<<<grid, 256, 0, s>>>(pool, pool_stride, k, k_stride, n_rows, row_ptr, row_node, korig, dest,
+                                             tau_dest, tau0, tau0_stride, errflag);
+}
+
+// dense: one CTA per row of K.  Front 0 holds every intermediate (+ A ∪ B as its update set); entries between two
+// kept nodes go to the root front.
+__global__ void __launch_bounds__(256)
+ingest_dense_kernel(double *pool, long long pool_stride, const double *K, int n, const int *pos, int nI,
+                    DFront f0, DFront root, double *tau0, int *errflag) {
+    const int u = blockIdx.x;
+    const long long b = blockIdx.y;
+    const double *row = K + (b * n + u) * (long long)n;
+    double *P = pool + b * pool_stride;
+    __shared__ double red[8];
+    __shared__ double tau_s;
+    double s = 0.0;
+    for (int v = threadIdx.x; v < n; v += 256) s += row[v];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        const double tau = 1.0 / t;
+        if (!(t > 0.0) || isinf(tau)) atomicOr(errflag, 2);
+        tau_s = tau;
+        tau0[b * n + u] = tau;
+        const int pu = pos[u];
+        if (pu < nI) P[f0.off + (long long)pu * f0.ld + f0.f] = tau;
+        else P[root.off + (long long)(pu - nI) * root.ld + root.f] = tau;
+    }
+    __syncthreads();
+    const double tau = tau_s;
+    const int pu = pos[u];
+    for (int v = threadIdx.x; v < n; v += 256) {
+        const int pv = pos[v];
+        const double val = row[v] * tau;
+        if (pu < nI || pv < nI) P[f0.off + (long long)pu * f0.ld + pv] = val;
+        else P[root.off + (long long)(pu - nI) * root.ld + (pv - nI)] = val;
+    }
+}
+
+void launch_ingest_dense(double *pool, long long pool_stride, int nbatch, const double *K, int n, const int *pos,
+                         int nI, DFront f0, DFront root, double *tau0, int *errflag, cudaStream_t s) {
+    dim3 grid(n, nbatch);
+    ingest_dense_kernel<<<grid, 256, 0, s>>>(pool, pool_stride, K, n, pos, nI, f0, root, tau0, errflag);
+}
+
+// =====================================================================================================
+// assembly (extend-add): parent[rel[i], rel[j]] += child[k+i, k+j];  parent tau col += child delta-tau col
+// grid (row tiles of 8, child, network); threads sweep the columns (coalesced reads of the child)
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+extend_add_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, const int *rel,
+                  const long long *rel_off) {
+    const int cid = ids[blockIdx.y];
+    const DFront C = fronts[cid];
+    const int m = C.f - C.k;
+    const int i0 = blockIdx.x * 8;
+    if (i0 >= m) return;
+    const DFront Pf = fronts[C.parent];
+    double *base = pool + (long long)blockIdx.z * pool_stride;
+    const double *Cm = base + C.off;
+    double *Pm = base + Pf.off;
+    const int *rl = rel + rel_off[cid];
+    const int wr = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = i0 + wr;
+    if (i >= m) return;
+    const double *crow = Cm + (long long)(C.k + i) * C.ld + C.k;
+    double *prow = Pm + (long long)rl[i] * Pf.ld;
+    for (int jx = lane; jx <= m; jx += 32) {
+        const double v = crow[jx];
+        const int pc = (jx < m) ? rl[jx] : Pf.f;
+        if (v != 0.0) prow[pc] += v;
+    }
+}
+
+void launch_extend_add(const LaunchCtx &c, const int *ids, int nchild, int max_m, const int *rel,
+                       const long long *rel_off) {
+    if (nchild <= 0 || max_m <= 0) return;
+    dim3 grid((max_m + 7) / 8, nchild, c.nbatch);
+    extend_add_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, rel, rel_off);
+}
+
+// =====================================================================================================
+// phase 2 (reference ngt.hpp:362-431): for every a of a group, eliminate the rest of the group.
+// Task front (order ng+1): rows/cols 0..ng-2 = group minus a, row ng-1 = a, column ng = all mass into the
+// other group (collapsed), column ng+1 = tau.  Eliminating its ng-1 pivots with the ordinary front kernels
+// leaves 1-P'_aa in (ng-1, ng) and tau'_a in (ng-1, ng+1).
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+phase2_gather_kernel(const double *pool, long long pool_stride, DFront root, int g0, int ng, int o0, int no,
+                     double *p2pool, long long p2_stride, const DFront *p2fronts, int task0, int rank, int nranks) {
+    const int t = blockIdx.y;            // task within the group = index of a
+    if (nranks > 1 && (t % nranks) != rank) return;
+    const int lr = blockIdx.x;           // local row of the task front (0..ng-1)
+    const DFront T = p2fronts[task0 + t];
+    const double *R = pool + (long long)blockIdx.z * pool_stride + root.off;
+    double *M = p2pool + (long long)blockIdx.z * p2_stride + T.off;
+    // local index -> group member: members other than a keep root order, a goes last
+    const int gr = (lr == ng - 1) ? t : (lr < t ? lr : lr + 1);
+    const double *src = R + (long long)(g0 + gr) * root.ld;
+    double *dst = M + (long long)lr * T.ld;
+    for (int lc = threadIdx.x; lc < ng; lc += 256) {
+        const int gc = (lc == ng - 1) ? t : (lc < t ? lc : lc + 1);
+        dst[lc] = (lc == lr) ? 0.0 : src[g0 + gc];
+    }
+    // mass into the other group, summed in a fixed order by warp 0
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        for (int c = threadIdx.x; c < no; c += 32) s += src[o0 + c];
+        s = warp_sum(s);
+        if (threadIdx.x == 0) {
+            dst[ng] = s;
+            dst[ng + 1] = src[root.f];
+        }
+    }
+    // the collapsed "other" node is row ng of the task front: never read (it is not a pivot), keep zero
+    if (lr == 0)
+        for (int lc = threadIdx.x; lc < ng + 2; lc += 256) M[(long long)ng * T.ld + lc] = 0.0;
+}
+
+void launch_phase2_gather(const LaunchCtx &c, DFront root, int g0, int ng, int o0, int no, double *p2pool,
+                          long long p2_stride, const DFront *p2fronts, int task0, int ntask, int rank, int nranks) {
+    if (ntask <= 0) return;
+    dim3 grid(ng, ntask, c.nbatch);
+    phase2_gather_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, root, g0, ng, o0, no, p2pool, p2_stride,
+                                                     p2fronts, task0, rank, nranks);
+}
+
+__global__ void phase2_collect_kernel(const double *p2pool, long long p2_stride, const DFront *p2fronts, int task0,
+                                      int ntask, int ng, double *om, double *tau, int out_stride, int out_off,
+                                      int rank, int nranks) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntask) return;
+    const long long b = blockIdx.y;
+    double o = 0.0, tt = 0.0;
+    if (nranks <= 1 || (t % nranks) == rank) {
+        const DFront T = p2fronts[task0 + t];
+        const double *M = p2pool + b * p2_stride + T.off;
+        o = M[(long long)(ng - 1) * T.ld + ng];
+        tt = M[(long long)(ng - 1) * T.ld + ng + 1];
+    }
+    om[b * out_stride + out_off + t] = o;
+    tau[b * out_stride + out_off + t] = tt;
+}
+
+void launch_phase2_collect(const LaunchCtx &c, const double *p2pool, long long p2_stride, const DFront *p2fronts,
+                           int task0, int ntask, int ng, double *om, double *tau, int out_stride, int out_off,
+                           int rank, int nranks) {
+    if (ntask <= 0) return;
+    dim3 grid((ntask + 127) / 128, c.nbatch);
+    phase2_collect_kernel<<<grid, 128, 0, c.stream>>>(p2pool, p2_stride, p2fronts, task0, ntask, ng, om, tau,
+                                                     out_stride, out_off, rank, nranks);
+}
+
+// =====================================================================================================
+// back-substitution (committors q and mean first-passage times t to A ∪ B for every eliminated node):
+//   q_X = U' q_R,  t_X = tau'_X + U' t_R     with U' = rows X of the eliminated front, R = everything later.
+// One CTA per (row of the current panel, front, network); panels are swept in reverse by the host.
+// x holds (q, t) interleaved per elimination position.
+// =====================================================================================================
+__global__ void __launch_bounds__(128)
+backsub_kernel(const double *pool, long long pool_stride, const DFront *fronts, const int *ids, const int *fidx,
+               const long long *idx_off, double *x, long long x_stride, int j) {
+    const int fid = ids[blockIdx.y];
+    const DFront F = fronts[fid];
+    if (j >= F.k) return;
+    const int nbp = min(NB_INNER, F.k - j);
+    const int r = blockIdx.x;
+    if (r >= nbp) return;
+    const int je = j + nbp;
+    const double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
+    double *xb = x + (long long)blockIdx.z * x_stride;
+    const int *idx = fidx + idx_off[fid];
+    const double *row = M + (long long)(j + r) * F.ld;
+    double q = 0.0, t = 0.0;
+    for (int c = je + threadIdx.x; c < F.f; c += 128) {
+        const double u = row[c];
+        const long long p = idx[c];
+        q += u * xb[2 * p];
+        t += u * xb[2 * p + 1];
+    }
+    __shared__ double rq[4], rt[4];
+    q = warp_sum(q);
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) { rq[threadIdx.x >> 5] = q; rt[threadIdx.x >> 5] = t; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const long long p = idx[j + r];
+        xb[2 * p] = rq[0] + rq[1] + rq[2] + rq[3];
+        xb[2 * p + 1] = rt[0] + rt[1] + rt[2] + rt[3] + row[F.f];
+    }
+}
+
+void launch_backsub_step(const LaunchCtx &c, const int *ids, int nfb, const int *fidx, const long long *idx_off,
+                         double *x, long long x_stride, int j) {
+    dim3 grid(NB_INNER, nfb, c.nbatch);
+    backsub_kernel<<<grid, 128, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, fidx, idx_off, x, x_stride, j);
+}
+
+}  // namespace ngt

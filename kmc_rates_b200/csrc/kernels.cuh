@@ -1,0 +1,111 @@
+// Device-side data layout and kernel launchers of the multifrontal NGT engine (sm_100a).
+//
+// HBM layout
+//   pool            one allocation of `nbatch * pool_stride` doubles.  Network b owns
+//                   pool[b*pool_stride ...]; inside it front F is a row-major f x ld matrix at F.off:
+//                     rows/cols 0..k-1      pivots (nodes this front eliminates, in elimination order)
+//                     rows/cols k..f-1      update set (later nodes the pivots touch)
+//                     column f              tau: tau_x of a pivot row, accumulated delta-tau of an update row
+//                   ld = roundup(f+1, 8) so every row starts 64-byte aligned.
+//   Eliminating the pivots of a front is exactly the reference's remove_node loop restricted to
+//   that front (reference source/kmc_rates/ngt.hpp:295-333), blocked:
+//     panel X of nb pivots:  W = (I - P_XX)^-1 by subtraction-free Gauss-Jordan, pivots
+//                            1-P_xx = sum of the off-diagonal row (ngt.hpp:222-238 does this only for
+//                            P_xx >= 0.99; Wales' GTH form is used always here)
+//                            U' = W [P_XR | tau_X]                      (panel_kernel, rowpanel_kernel)
+//     Schur update:          P_RR += P_RX U' ,  tau_R += P_RX tau'_X    (update kernels, FP64 DMMA)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ngt {
+
+constexpr int NB_INNER = 32;    // pivots per panel (in-SM Gauss-Jordan block)
+constexpr int NB_OUTER = 128;   // pivots per delayed trailing update (K of the big Schur GEMM)
+
+struct DFront {
+    long long off;   // offset in the pool (doubles)
+    int f, k, ld;    // order, pivots, leading dimension
+    int parent;      // front id or -1
+};
+
+enum UpdateMode { MODE_A = 0, MODE_B = 1, MODE_D = 2 };
+
+struct Region { int r0, r1, c0, c1, k0, k1; };
+
+// Rows / columns / pivot range touched by one Schur-update launch (see kernels.cuh).
+//   MODE_A: column panel inside the outer block      rows [je,f)  cols [je,JE)   K = [j,je)
+//   MODE_B: row panel of the remaining outer pivots  rows [je,JE) cols [JE,f]    K = [j,je)
+//   MODE_D: delayed trailing update                  rows [JE,f)  cols [JE,f]    K = [J,JE)
+// column f is the tau column, so "cols [..,f]" means c1 = f+1.
+__host__ __device__ inline bool get_region(int f, int k, int j, int mode, Region &R) {
+    if (j >= k) return false;
+    const int je = (j + NB_INNER < k ? j + NB_INNER : k);
+    const int J = (j / NB_OUTER) * NB_OUTER;
+    const int JE = (J + NB_OUTER < k ? J + NB_OUTER : k);
+    if (mode == MODE_A) { R.r0 = je; R.r1 = f; R.c0 = je; R.c1 = JE; R.k0 = j; R.k1 = je; }
+    else if (mode == MODE_B) { R.r0 = je; R.r1 = JE; R.c0 = JE; R.c1 = f + 1; R.k0 = j; R.k1 = je; }
+    else {
+        if (je != JE) return false;   // the delayed update runs once, after the last panel of the outer block
+        R.r0 = JE; R.r1 = f; R.c0 = JE; R.c1 = f + 1; R.k0 = J; R.k1 = JE;
+    }
+    return R.r1 > R.r0 && R.c1 > R.c0;
+}
+
+
+struct LaunchCtx {
+    double *pool;
+    long long pool_stride;
+    int nbatch;
+    const DFront *fronts;     // device array of all fronts
+    double *wbuf;             // nbatch * maxfb * NB_INNER*NB_INNER
+    int maxfb;                // fronts per batch upper bound (stride of wbuf)
+    int *errflag;             // device int
+    cudaStream_t stream;
+    int gemm_path;            // 0 DMMA, 1 DFMA
+};
+
+// ids: device array of front ids in this batch (nfb of them).
+void launch_panel(const LaunchCtx &c, const int *ids, int nfb, int j);
+void launch_rowpanel(const LaunchCtx &c, const int *ids, int nfb, int j, int max_cols);
+// max_tiles: upper bound of tiles over the fronts of the batch for this (j, mode); computed by the host.
+void launch_update(const LaunchCtx &c, const int *ids, int nfb, int j, int mode, int max_tiles);
+
+// tile geometry used by the host to size grids
+int update_tile_m(int gemm_path);
+int update_tile_n(int gemm_path);
+
+// ---- ingest ---------------------------------------------------------------------------------------
+// sparse: CSR by source node; korig[e] = index of entry e in the caller's k array; dest[e] = pool offset
+void launch_ingest_sparse(double *pool, long long pool_stride, int nbatch, const double *k, long long k_stride,
+                          int n_rows, const long long *row_ptr, const int *row_node, const int *korig,
+                          const long long *dest, const long long *tau_dest, double *tau0, long long tau0_stride,
+                          int *errflag, cudaStream_t s);
+// dense: K is nbatch x n x n row-major; pos = node -> elimination position; front 0 = all intermediates (k0 = nI),
+// root = last front
+void launch_ingest_dense(double *pool, long long pool_stride, int nbatch, const double *K, int n, const int *pos,
+                         int nI, DFront f0, DFront root, double *tau0, int *errflag, cudaStream_t s);
+
+// ---- assembly: child update blocks (+ delta-tau column) are added into their parents ---------------
+// ids: children of one round (all have distinct parents); rel/rel_off: local index of child update row in parent
+void launch_extend_add(const LaunchCtx &c, const int *ids, int nchild, int max_m, const int *rel,
+                       const long long *rel_off);
+
+// ---- phase 2: build one front per a in the group from the reduced root block -----------------------
+// group = [g0, g0+ng) rows of the root, other = the remaining root rows.  Task t (a = g0 + t) gets a front of
+// order ng+1: pivots = group minus a (root order), then a, then the collapsed "other" column; tau in column ng+1.
+void launch_phase2_gather(const LaunchCtx &c, DFront root, int g0, int ng, int o0, int no,
+                          double *p2pool, long long p2_stride, const DFront *p2fronts, int task0, int ntask,
+                          int rank, int nranks);
+// read 1-P'_aa (row ng-1, col ng) and tau'_a (row ng-1, col ng+1) of every task front
+void launch_phase2_collect(const LaunchCtx &c, const double *p2pool, long long p2_stride, const DFront *p2fronts,
+                           int task0, int ntask, int ng, double *om, double *tau, int out_stride, int out_off,
+                           int rank, int nranks);
+
+// ---- committor / MFPT back-substitution over kept factors -------------------------------------------
+// x is nbatch x npos x 2 (q, t interleaved) indexed by elimination position; one call handles the panel that
+// starts at pivot j of every front in `ids`; the host sweeps levels top-down and panels in reverse.
+void launch_backsub_step(const LaunchCtx &c, const int *ids, int nfb, const int *fidx, const long long *idx_off,
+                         double *x, long long x_stride, int j);
+
+}  // namespace ngt

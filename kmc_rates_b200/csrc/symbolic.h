@@ -1,0 +1,83 @@
+// Host-side symbolic analysis for the multifrontal NGT engine.
+//
+// The reference keeps a pointer graph and discovers fill-in edge by edge while it eliminates
+// (reference source/kmc_rates/graph.hpp:222-236, ngt.hpp:271-276) and re-sorts the node list by degree
+// every step (ngt.hpp:192-200).  Here the whole elimination is planned up front:
+//   * a nested-dissection ordering of the intermediate nodes (A ∪ B are ordered last and never
+//     eliminated in phase 1),
+//   * supernodes = the separators and leaves of the dissection tree,
+//   * one dense "front" per supernode: its k pivots followed by the m later nodes it touches,
+//   * an assembly tree (parent = front owning the earliest node of the update set), levels and
+//     batches of fronts that are eliminated by the same kernel launches.
+// No arithmetic happens here; the numeric phase never allocates.
+#pragma once
+#include <cstdint>
+#include <vector>
+#include <string>
+
+namespace ngt {
+
+struct Front {
+    int32_t k;        // pivots eliminated in this front
+    int32_t m;        // update-set size (later nodes touched)
+    int32_t f;        // k + m
+    int32_t ld;       // leading dimension in doubles (>= f + 1; column f carries tau)
+    int64_t off;      // offset of the front's matrix in the pool (doubles)
+    int64_t idx_off;  // offset of its index list (elimination positions; pivots then sorted update set)
+    int32_t level;    // 0 = leaf of the assembly tree
+    int32_t parent;   // front id, or -1 (no later node touched: component not connected to A ∪ B)
+    int32_t first;    // elimination position of its first pivot
+    int32_t pad;
+};
+
+struct Batch {
+    int32_t level;
+    int32_t max_k, max_f;
+    std::vector<int32_t> fronts;   // front ids processed by the same launches
+};
+
+struct Symbolic {
+    int64_t n = 0;          // nodes (dense ids)
+    int64_t nI = 0;         // intermediates = nodes eliminated in phase 1
+    int64_t nA = 0, nB = 0;
+    std::vector<int32_t> pos;       // node id -> elimination position (A then B occupy nI..n-1); -1 = node absent
+    std::vector<int32_t> node_at;   // elimination position -> node id
+    std::vector<Front> fronts;      // fronts[root_id] is the root (k = 0, index list = A ∪ B)
+    int32_t root_id = -1;
+    std::vector<int32_t> fidx;      // concatenated index lists
+    std::vector<int64_t> child_ptr; // CSR of children per front
+    std::vector<int32_t> child_ids;
+    std::vector<int64_t> rel_off;   // per front: offset into rel (m entries): local index in the parent
+    std::vector<int32_t> rel;
+    std::vector<int32_t> pos_front; // elimination position -> owning front (pivot owner, root for A ∪ B)
+    std::vector<Batch> batches;     // in execution order (by level)
+    int64_t pool_doubles = 0;
+    int32_t n_levels = 0;
+    int32_t max_front = 0;
+    double alg_flops = 0, alg_bytes = 0, schur_flops = 0;
+};
+
+// Undirected structure in CSR (no self loops, deduplicated, symmetrised).
+struct Adjacency {
+    int64_t n = 0;
+    std::vector<int64_t> ptr;
+    std::vector<int32_t> adj;
+};
+
+// Build the symmetrised adjacency of the rate graph.
+void build_adjacency(int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, Adjacency &g);
+
+// Sparse network: nested dissection + supernodal symbolic factorisation.
+// present[u] = 0 marks ids that appear in no rate (they are ignored, like the reference which only
+// creates nodes named by a rate, ngt.hpp:114-117).
+void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
+                    const std::vector<int64_t> &A, const std::vector<int64_t> &B,
+                    int leaf_size, Symbolic &S);
+
+// Complete network: one front holding every intermediate, plus the root.
+void analyse_dense(int64_t n, const std::vector<int64_t> &A, const std::vector<int64_t> &B, Symbolic &S);
+
+// Local index of elimination position p inside front fr (pivot range or binary search of the update set); -1 if absent.
+int32_t local_index(const Symbolic &S, int32_t fr, int32_t p);
+
+}  // namespace ngt

@@ -1,0 +1,127 @@
+"""GPU tests of the drop-in Python API; they read like the reference's own tests
+(reference kmc_rates/tests/test_graph_transformation.py, test_cpp_ngt.py, test_kmc.py)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _three_state_rates():
+    return {(i, j): 1.0 for i in range(3) for j in range(3) if i != j}
+
+
+@pytest.mark.parametrize("i,j", [(0, 1), (1, 2), (0, 2)])
+def test_graph_reduction_three_state(i, j):
+    """reference test_graph_transformation.py:73-98"""
+    from kmc_rates_b200 import GraphReduction
+    reducer = GraphReduction(_three_state_rates(), [i], [j], debug=True)
+    reducer.check_graph()
+    reducer.compute_rates()
+    rAB = reducer.get_rate_AB()
+    rBA = reducer.get_rate_BA()
+    reducer.check_graph()
+    assert reducer.graph.number_of_nodes() == 2
+    assert reducer.graph.number_of_edges() == 4
+    assert abs(rAB - 1.0) < 1e-7 and abs(rBA - 1.0) < 1e-7
+    assert abs(reducer.get_rate_AB_SS() - 1.5) < 1e-7
+
+
+@pytest.mark.parametrize("A,B", [([0], [1]), ([0, 1, 2], [3]), ([0, 1, 2], [3, 4, 5, 6])])
+def test_graph_reduction_random(A, B):
+    """reference test_graph_transformation.py:100-124, with the oracle as the value check"""
+    from kmc_rates_b200 import GraphReduction, synth
+    from oracle.py_ngt import PyGraphReduction
+    rates = synth.random_connected_graph(20, 20, A + B, seed=len(A) + 10 * len(B))
+    reducer = GraphReduction(rates, A, B)
+    reducer.check_graph()
+    reducer.compute_rates()
+    reducer.check_graph()
+    assert reducer.graph.number_of_nodes() == len(A) + len(B)
+    if len(A) == 1 and len(B) == 1:
+        assert reducer.graph.number_of_edges() <= 4
+    ref = PyGraphReduction(rates, A, B)
+    ref.compute_rates()
+    assert abs(reducer.get_rate_AB() - ref.get_rate_AB()) < 1e-9 * ref.get_rate_AB()
+    assert abs(reducer.get_rate_BA() - ref.get_rate_BA()) < 1e-9 * ref.get_rate_BA()
+    assert abs(reducer.get_rate_AB_SS() - ref.get_rate_AB_SS()) < 1e-9 * ref.get_rate_AB_SS()
+    for a in A:
+        assert abs(reducer.get_committor_probabilityAB(a) - ref.get_committor_probabilityAB(a)) < 1e-9
+
+
+def test_graph_reduction_committors_weights_and_groups():
+    """reference test_kmc.py:74-115: groups, weights, committors of nodes inside and outside A ∪ B"""
+    from kmc_rates_b200 import GraphReduction, synth
+    from oracle.py_ngt import PyGraphReduction
+    A, B = [0, 1, 2, 3], [8, 9]
+    rates = synth.random_connected_graph(10, 20, A + B + [5], seed=3)
+    rng = np.random.RandomState(0)
+    weights = {x: rng.uniform(0, 1) for x in A + B}
+    reducer = GraphReduction(rates, A, B, weights=weights)
+    ref = PyGraphReduction(rates, A, B, weights=weights)
+    nodes = set(A + B + [5])
+    got = reducer.compute_committor_probabilities(nodes)
+    want = ref.compute_committor_probabilities(nodes)
+    for x in nodes:
+        assert abs(got[x] - want[x]) < 1e-9
+    assert abs(reducer.compute_committor_probability(5) - want[5]) < 1e-9
+    reducer.compute_rates()
+    ref.compute_rates()
+    assert abs(reducer.get_rate_AB() - ref.get_rate_AB()) < 1e-9 * ref.get_rate_AB()
+    assert abs(reducer.get_rate_BA() - ref.get_rate_BA()) < 1e-9 * ref.get_rate_BA()
+
+
+def test_graph_reduction_accepts_graph_and_tuple_labels():
+    """README passes a graph (reference README.rst:28-33); the lattice example uses tuple labels
+    (reference examples/example_committor_probabilities.py:8-21)"""
+    import networkx as nx
+    from kmc_rates_b200 import GraphReduction, kmcgraph_from_rates
+    from oracle.py_ngt import PyGraphReduction
+    rng = np.random.RandomState(1)
+    grid = nx.grid_graph([5, 5])
+    rates = {}
+    for u, v in grid.edges():
+        rates[(u, v)] = rng.rand()
+        rates[(v, u)] = rng.rand()
+    A, B = [(0, 0)], [(4, 4)]
+    reducer = GraphReduction(kmcgraph_from_rates(rates), A, B)
+    com = reducer.compute_committor_probabilities(list(grid.nodes()))
+    ref = PyGraphReduction(rates, A, B)
+    want = ref.compute_committor_probabilities(list(grid.nodes()))
+    for x in grid.nodes():
+        assert abs(com[x] - want[x]) < 1e-9
+    reducer.compute_rates()
+    ref.compute_rates()
+    assert abs(reducer.get_rate_AB() - ref.get_rate_AB()) < 1e-9 * ref.get_rate_AB()
+
+
+def test_graph_reduction_errors():
+    """error conventions of reference _kmc_rates.py:148-154, 434-447"""
+    from kmc_rates_b200 import GraphReduction, synth
+    rates = synth.to_dict(*synth.complete_deterministic(5))
+    with pytest.raises(ValueError):
+        GraphReduction(rates, [0, 1], [1, 2])
+    with pytest.raises(ValueError):
+        GraphReduction(rates, [0], [17])
+    red = GraphReduction(rates, [0], [1])
+    with pytest.raises(RuntimeError):
+        red.get_committor_probabilityAB(0)
+    red.compute_rates()
+    with pytest.raises(ValueError):
+        red.get_committor_probabilityAB(3)
+    # disconnected A and B
+    r2 = {(0, 1): 1.0, (1, 0): 1.0, (2, 3): 1.0, (3, 2): 1.0}
+    with pytest.raises(ValueError):
+        GraphReduction(r2, [0], [2])
+
+
+def test_ngt_class_matches_reference_tests():
+    """reference kmc_rates/tests/test_cpp_ngt.py:37-63 (NGT10 through the NGT class, dict input)"""
+    from kmc_rates_b200 import NGT, synth
+    rates = synth.to_dict(*synth.complete_deterministic(10))
+    reducer = NGT(rates, [0, 1, 2], [3, 4, 5], debug=False)
+    reducer.compute_rates()
+    assert abs(reducer.get_rate_AB() - 5.1013138820442565) < 1e-7
+    assert abs(reducer.get_rate_BA() - 3) < 1e-7
+    assert abs(reducer.get_rate_AB_SS() - 19.933950145409426) < 1e-7
+    assert abs(reducer.get_rate_BA_SS() - 6.970856553435547) < 1e-7
+    assert reducer.time_solve > 0
