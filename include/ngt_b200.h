@@ -50,7 +50,7 @@ enum {
 /* Options (0 = default everywhere). */
 typedef struct ngt_options {
     int32_t device;          /* CUDA device ordinal */
-    int32_t gemm_path;       /* 0 = FP64 tensor-core DMMA (default), 1 = scalar DFMA (debug / cross-check) */
+    int32_t gemm_path;       /* 0 = FP64 tensor-core DMMA, tile chosen per launch (default); 1 = scalar DFMA (cross-check); 2 = DMMA 128x128 cp.async kernel everywhere */
     int32_t leaf_size;       /* nested-dissection leaf size (0 -> 64) */
     int32_t keep_factor;     /* 1 = keep eliminated rows for committor back-substitution */
     int32_t phase2_closed_form; /* 1 = also evaluate phase 2 by the closed form 1/G_aa as a cross-check */
@@ -108,6 +108,12 @@ typedef struct ngt_stats {
     double  reserved[8];
 } ngt_stats;
 int ngt_get_stats(ngt_handle h, ngt_stats *st);
+/* Device-timed repetition for bench.py: `steps` x (ingest + phase 1 + phase 2) enqueued back to back on the
+ * engine's stream, bracketed by CUDA events on that stream; results of the last step are then downloaded. */
+int ngt_timed_steps(ngt_handle h, int32_t steps, double *ms_total);
+/* One phase-1 pass with CUDA events around every Schur-update launch: total kernel time (ms), the flops those
+ * launches performed, and their count.  Slower than a plain pass; never used inside a timed region. */
+int ngt_profile_schur(ngt_handle h, double *ms_schur, double *flops, int64_t *launches);
 
 /* ---- batched networks sharing one topology (temperature sweeps) --------------------------- */
 /* k is nbatch x nnz (row-major): network b uses k[b*nnz .. (b+1)*nnz). */

@@ -84,6 +84,8 @@ def lib():
         "ngt_get_committors": [H, _f64p],
         "ngt_get_mfpt": [H, _f64p],
         "ngt_get_stats": [H, ctypes.POINTER(Stats)],
+        "ngt_timed_steps": [H, ctypes.c_int32, _f64p],
+        "ngt_profile_schur": [H, _f64p, _f64p, _i64p],
         "ngt_batch_create": [i64, i64, i64, _i64p, _i64p, vp, i64, _i64p, i64, _i64p, OP, HP],
         "ngt_batch_create_dense": [i64, i64, vp, i64, _i64p, i64, _i64p, OP, HP],
         "ngt_batch_create_dense_dev": [i64, i64, vp, i64, _i64p, i64, _i64p, OP, HP],
@@ -108,7 +110,7 @@ EXPORTED_SYMBOLS = [
     "ngt_create", "ngt_create_dense", "ngt_create_dense_dev", "ngt_set_rates", "ngt_set_rates_dev", "ngt_set_weights",
     "ngt_destroy", "ngt_compute_rates", "ngt_compute_rates_and_committors", "ngt_phase_one", "ngt_phase_two",
     "ngt_get_rates", "ngt_get_final", "ngt_get_reduced", "ngt_get_initial_tau", "ngt_get_committors", "ngt_get_mfpt",
-    "ngt_get_stats", "ngt_batch_create", "ngt_batch_create_dense", "ngt_batch_create_dense_dev", "ngt_batch_get_rates",
+    "ngt_get_stats", "ngt_timed_steps", "ngt_profile_schur", "ngt_batch_create", "ngt_batch_create_dense", "ngt_batch_create_dense_dev", "ngt_batch_get_rates",
     "ngt_reduced_block_dev", "ngt_phase_two_shard", "ngt_set_final", "ngt_last_error", "ngt_version",
 ]
 
@@ -302,6 +304,18 @@ class Handle(object):
         s = Stats()
         check(lib().ngt_get_stats(self.h, ctypes.byref(s)))
         return s.as_dict()
+
+    def timed_steps(self, steps):
+        """device time (ms, CUDA events on the engine's stream) of `steps` x (ingest + phase 1 + phase 2)"""
+        ms = ctypes.c_double()
+        check(lib().ngt_timed_steps(self.h, int(steps), ctypes.byref(ms)))
+        return ms.value
+
+    def profile_schur(self):
+        """(ms, flops, launches) of the Schur-update kernel over one phase-1 pass"""
+        ms, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        check(lib().ngt_profile_schur(self.h, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n)))
+        return ms.value, fl.value, n.value
 
     def reduced_block_dev(self):
         p = ctypes.c_void_p()

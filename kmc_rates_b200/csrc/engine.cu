@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -102,8 +103,8 @@ struct Engine {
     // device: values
     DevBuf<double> d_pool;
     long long pool_stride = 0;
-    DevBuf<double> d_wbuf;
-    int maxfb = 1;
+    DevBuf<double> d_wbuf, d_rsbuf;
+    int maxfb = 1, maxchunks = 1;
     DevBuf<int> d_err;
     DevBuf<double> d_tau0;
     // sparse ingest
@@ -134,12 +135,34 @@ struct Engine {
     std::vector<double> xq;         // nbatch x npos x 2
     bool have_phase1 = false, have_phase2 = false, have_backsub = false, values_loaded = false;
 
+    bool use_big_kernel = std::getenv("NGT_B200_BIG") != nullptr;   // 128 x 128 kernel: measured slower than 2 CTAs/SM of 128 x 64
+    bool use_lookahead = std::getenv("NGT_B200_NO_LOOKAHEAD") == nullptr;
+    bool d2_pending = false;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t sync_ev[2] = {nullptr, nullptr};
+    cudaEvent_t sync_event(int i) { return sync_ev[i]; }
+    bool profile_schur = false;
+    std::vector<cudaEvent_t> prof_ev;   // pairs around every update launch when profile_schur
+    size_t prof_used = 0;
+    cudaEvent_t prof_event() {
+        if (prof_used == prof_ev.size()) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            prof_ev.push_back(e);
+        }
+        return prof_ev[prof_used++];
+    }
+
     ngt_stats st{};
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     ~Engine() {
         for (auto &e : ev)
             if (e) cudaEventDestroy(e);
+        for (auto &e : prof_ev) cudaEventDestroy(e);
+        for (auto &e : sync_ev)
+            if (e) cudaEventDestroy(e);
+        if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -151,6 +174,8 @@ struct Engine {
         c.fronts = fr;
         c.wbuf = d_wbuf.p;
         c.maxfb = maxfb;
+        c.rsbuf = d_rsbuf.p;
+        c.maxchunks = maxchunks;
         c.errflag = d_err.p;
         c.stream = stream;
         c.gemm_path = opt.gemm_path;
@@ -167,7 +192,12 @@ struct Engine {
         device = opt.device;
         if (device < 0 || device >= ndev) throw InvalidError("device ordinal out of range");
         CK(cudaSetDevice(device));
-        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        // the panel chain is latency critical: its stream outranks the look-ahead stream of big trailing updates
+        int prio_lo = 0, prio_hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
+        CK(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, prio_lo));
+        for (auto &x : sync_ev) CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
         for (auto &x : ev) CK(cudaEventCreate(&x));
         d_err.alloc(1);
         CK(cudaMemset(d_err.p, 0, sizeof(int)));
@@ -267,6 +297,8 @@ struct Engine {
 
         build_phase2_structure();
         d_wbuf.alloc((size_t)nbatch * maxfb * ngt::NB_INNER * ngt::NB_INNER);
+        maxchunks = std::max(1, (S.max_front + ngt::RS_CHUNK - 1) / ngt::RS_CHUNK);
+        d_rsbuf.alloc((size_t)nbatch * maxfb * maxchunks * ngt::NB_INNER);
         d_om.alloc((size_t)nbatch * m);
         d_ftau.alloc((size_t)nbatch * m);
 
@@ -341,22 +373,76 @@ struct Engine {
         const int tm = ngt::update_tile_m(opt.gemm_path), tn = ngt::update_tile_n(opt.gemm_path);
         const int *ids = dev_ids + b.dev_off;
         for (int j = 0; j < b.max_k; j += ngt::NB_INNER) {
-            ngt::launch_panel(c, ids, nfb, j);
-            int max_cols = 0;
+            int max_cols = 0;   // columns right of the panel incl. the tau column, widest live front
             for (int i = 0; i < nfb; ++i)
                 if (b.k[i] > j) max_cols = std::max(max_cols, b.f[i] + 1 - std::min(j + ngt::NB_INNER, b.k[i]));
-            ngt::launch_rowpanel(c, ids, nfb, j, max_cols);
-            st.n_launches += 2;
-            for (int mode = 0; mode < 3; ++mode) {
-                double fl = 0;
-                const int mt = max_tiles(b, j, mode, tm, tn, fl);
-                st.schur_flops += fl * nbatch;
-                if (mt > 0) {
-                    ngt::launch_update(c, ids, nfb, j, mode, mt);
-                    st.n_launches++;
+            if (max_cols - 1 > ngt::RS_SPLIT) {
+                ngt::launch_rowsum(c, ids, nfb, j, max_cols - 1);
+                st.n_launches++;
+            }
+            ngt::launch_panel(c, ids, nfb, j);
+            st.n_launches++;
+            if (max_cols > ngt::FUSE_COLS) {
+                ngt::launch_rowpanel(c, ids, nfb, j, max_cols);
+                st.n_launches++;
+            }
+            double fl = 0, dummy = 0;
+            const int ta = max_tiles(b, j, ngt::MODE_A, tm, tn, fl);
+            const int tb = max_tiles(b, j, ngt::MODE_B, tm, tn, fl);
+            const int td1a = max_tiles(b, j, ngt::MODE_D1A, tm, tn, fl);
+            const int td1b = max_tiles(b, j, ngt::MODE_D1B, tm, tn, fl);
+            int td2 = max_tiles(b, j, ngt::MODE_D2, tm, tn, fl);
+            st.schur_flops += fl * nbatch;
+            // large trailing regions run on the 128 x 128 kernel when they fill the machine (>= 2 waves of big
+            // tiles); small regions keep the 128 x 64 kernel (more CTAs)
+            ngt::LaunchCtx c2 = c;
+            bool d2_async = false;
+            if (td2 > 0) {
+                long long live = 0;
+                for (int i = 0; i < nfb; ++i) live += (b.k[i] > j);
+                const int tbig = max_tiles(b, j, ngt::MODE_D2, ngt::update_tile_m(2), ngt::update_tile_n(2), dummy);
+                if (opt.gemm_path == 0 && use_big_kernel && (long long)tbig * live * nbatch >= 2 * 148) {
+                    c2.gemm_path = 2;
+                    td2 = tbig;
+                }
+                // look-ahead: a trailing update big enough to keep the GPU busy runs on the second stream while
+                // the next outer block's panels proceed on the main stream
+                d2_async = use_lookahead && (long long)td2 * live * nbatch >= 148;
+            }
+            auto timed = [&](cudaStream_t sx, auto &&fn) {
+                if (profile_schur) CK(cudaEventRecord(prof_event(), sx));
+                fn();
+                if (profile_schur) CK(cudaEventRecord(prof_event(), sx));
+                st.n_launches++;
+                st.reserved[0] += 1;   // Schur-update launches
+            };
+            if (ta + tb > 0) timed(stream, [&] { ngt::launch_update(c, ids, nfb, j, ngt::MODE_AB, ta + tb, ta); });
+            if (td1a + td1b + td2 > 0) {
+                if (d2_async) {
+                    // D2 needs the finished panels of this outer block ...
+                    CK(cudaEventRecord(sync_event(0), stream));
+                    CK(cudaStreamWaitEvent(stream2, sync_event(0), 0));
+                }
+                if (td1a + td1b > 0) {
+                    // ... D1 touches the region the previous D2 was writing
+                    if (d2_pending) { CK(cudaStreamWaitEvent(stream, sync_event(1), 0)); d2_pending = false; }
+                    timed(stream, [&] { ngt::launch_update(c, ids, nfb, j, ngt::MODE_D1, td1a + td1b, td1a); });
+                }
+                if (td2 > 0) {
+                    if (d2_async) {
+                        c2.stream = stream2;
+                        timed(stream2, [&] { ngt::launch_update(c2, ids, nfb, j, ngt::MODE_D2, td2, 0); });
+                        CK(cudaEventRecord(sync_event(1), stream2));
+                        d2_pending = true;
+                    } else {
+                        if (d2_pending) { CK(cudaStreamWaitEvent(stream, sync_event(1), 0)); d2_pending = false; }
+                        timed(stream, [&] { ngt::launch_update(c2, ids, nfb, j, ngt::MODE_D2, td2, 0); });
+                    }
                 }
             }
         }
+        // everything after this batch (assembly into parents, next level) reads what D2 wrote
+        if (d2_pending) { CK(cudaStreamWaitEvent(stream, sync_event(1), 0)); d2_pending = false; }
     }
 
     void check_errflag(const char *where) {
@@ -398,6 +484,8 @@ struct Engine {
         CK(cudaSetDevice(device));
         st.n_launches = 0;
         st.schur_flops = 0;
+        st.reserved[0] = 0;
+        prof_used = 0;
         CK(cudaEventRecord(ev[0], stream));
         ingest();
         CK(cudaEventRecord(ev[1], stream));
@@ -435,6 +523,11 @@ struct Engine {
     }
 
     void phase_two(int rank = 0, int nranks = 1) {
+        phase_two_enqueue(rank, nranks);
+        phase_two_finish(nranks);
+    }
+
+    void phase_two_enqueue(int rank = 0, int nranks = 1) {
         if (!have_phase1) throw StateError("phase_two called before phase_one");
         CK(cudaSetDevice(device));
         CK(cudaEventRecord(ev[3], stream));
@@ -472,6 +565,9 @@ struct Engine {
             st.n_launches++;
         }
         CK(cudaEventRecord(ev[4], stream));
+    }
+
+    void phase_two_finish(int nranks = 1) {
         final_om.resize((size_t)nbatch * m);
         final_tau.resize((size_t)nbatch * m);
         CK(cudaMemcpyAsync(final_om.data(), d_om.p, final_om.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -556,6 +652,7 @@ Engine *make_engine(const ngt_options *opt, int64_t nbatch) {
 void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, const double *k,
                   int64_t nA, const int64_t *A, int64_t nB, const int64_t *B) {
     auto t0 = std::chrono::steady_clock::now();
+    ngt::Timer tm;
     if (n <= 0 || nnz < 0) throw InvalidError("empty network");
     if (n > 2000000000LL) throw InvalidError("too many nodes");
     E->n = n;
@@ -576,10 +673,31 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
     for (int64_t u = 0; u < n; ++u)
         if (present[u] && outdeg[u + 1] == 0) throw InvalidError("node " + std::to_string(u) + " has no outgoing rate");
 
+    tm.lap("validate input");
     ngt::Adjacency g;
     ngt::build_adjacency(n, nnz, src, dst, g);
+    tm.lap("adjacency");
+    // Nodes with no (undirected) path to A ∪ B cannot influence any result; like the reference's Python front end
+    // (_kmc_rates.py:414-425) they are dropped before elimination.  Their committors read NaN.
+    {
+        std::vector<int32_t> stack;
+        std::vector<char> reach(n, 0);
+        for (int64_t a : E->A) if (!reach[a]) { reach[a] = 1; stack.push_back((int32_t)a); }
+        for (int64_t b : E->B) if (!reach[b]) { reach[b] = 1; stack.push_back((int32_t)b); }
+        while (!stack.empty()) {
+            const int32_t u = stack.back();
+            stack.pop_back();
+            for (int64_t e = g.ptr[u]; e < g.ptr[u + 1]; ++e) {
+                const int32_t v = g.adj[e];
+                if (!reach[v]) { reach[v] = 1; stack.push_back(v); }
+            }
+        }
+        for (int64_t u = 0; u < n; ++u) if (!reach[u]) present[u] = 0;
+    }
+    tm.lap("prune unreachable");
     ngt::analyse_sparse(g, present, E->A, E->B, E->opt.leaf_size, E->S);
     const Symbolic &S = E->S;
+    tm.lap("analyse_sparse total");
 
     // CSR by source over present nodes, (src,dst) duplicates resolved "last wins" (std::map semantics, ngt.pyx:76-81)
     for (int64_t u = 0; u < n; ++u) outdeg[u + 1] += outdeg[u];
@@ -615,18 +733,23 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
         tau_dest.push_back(F.off + (long long)lr * F.ld + F.f);
     }
     E->n_rows = (int)row_node.size();
+    tm.lap("CSR + slot table");
     E->init_device();
+    tm.lap("init device");
     E->d_row_ptr.upload(row_ptr);
     E->d_row_node.upload(row_node);
     E->d_korig.upload(korig);
     E->d_dest.upload(dest);
     E->d_tau_dest.upload(tau_dest);
+    tm.lap("upload ingest tables");
     E->upload_structure();
+    tm.lap("upload structure + alloc pools");
     E->d_k.alloc((size_t)nnz * E->nbatch);
     if (k) {
         CK(cudaMemcpy(E->d_k.p, k, (size_t)nnz * E->nbatch * sizeof(double), cudaMemcpyHostToDevice));
         E->values_loaded = true;
     }
+    tm.lap("upload rates");
     E->st.ms_symbolic = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
@@ -916,6 +1039,54 @@ int ngt_get_stats(ngt_handle h, ngt_stats *st) {
     return guard([&] {
         Engine *E = eng(h);
         *st = E->st;
+    });
+}
+
+int ngt_timed_steps(ngt_handle h, int32_t steps, double *ms_total) {
+    return guard([&] {
+        Engine *E = eng(h);
+        if (steps < 1) throw InvalidError("steps must be >= 1");
+        CK(cudaSetDevice(E->device));
+        CK(cudaStreamSynchronize(E->stream));
+        CK(cudaEventRecord(E->ev[5], E->stream));
+        for (int i = 0; i < steps; ++i) {
+            E->phase_one();
+            E->phase_two_enqueue();
+        }
+        cudaEvent_t stop = E->prof_event();
+        CK(cudaEventRecord(stop, E->stream));
+        CK(cudaStreamSynchronize(E->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, E->ev[5], stop));
+        *ms_total = ms;
+        E->phase_two_finish();
+    });
+}
+
+int ngt_profile_schur(ngt_handle h, double *ms_schur, double *flops, int64_t *launches) {
+    return guard([&] {
+        Engine *E = eng(h);
+        CK(cudaSetDevice(E->device));
+        E->profile_schur = true;
+        try {
+            E->phase_one();
+        } catch (...) {
+            E->profile_schur = false;
+            throw;
+        }
+        E->profile_schur = false;
+        CK(cudaStreamSynchronize(E->stream));
+        E->check_errflag("phase one");
+        double tot = 0;
+        for (size_t i = 0; i + 1 < E->prof_used; i += 2) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, E->prof_ev[i], E->prof_ev[i + 1]));
+            tot += ms;
+        }
+        E->st.ms_schur = tot;
+        *ms_schur = tot;
+        *flops = E->st.schur_flops;
+        *launches = (int64_t)(E->prof_used / 2);
     });
 }
 

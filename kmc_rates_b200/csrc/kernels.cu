@@ -16,13 +16,49 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // =====================================================================================================
-// panel kernel: one CTA (1024 threads, thread (u,q)) per front and network.
+// partial row sums for wide fronts: grid (column chunks, fronts, networks).  The panel kernel adds the
+// chunks in a fixed order, so results are deterministic.
+// =====================================================================================================
+__global__ void __launch_bounds__(1024)
+rowsum_kernel(const double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j,
+              double *rsbuf, int maxfb, int maxchunks) {
+    const DFront F = fronts[ids[blockIdx.y]];
+    if (j >= F.k) return;
+    const int nbp = min(NB_INNER, F.k - j);
+    const int je = j + nbp;
+    if (F.f - je <= RS_SPLIT) return;            // narrow front: the panel kernel sums its own rows
+    const int c0 = je + blockIdx.x * RS_CHUNK;
+    if (c0 >= F.f) return;
+    const int c1 = min(c0 + RS_CHUNK, F.f);
+    const double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
+    double *out = rsbuf + (((long long)blockIdx.z * maxfb + blockIdx.y) * maxchunks + blockIdx.x) * NB_INNER;
+    const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (r >= nbp) return;
+    const double *row = M + (long long)(j + r) * F.ld;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int c = c0 + lane;
+    for (; c + 96 < c1; c += 128) { s0 += row[c]; s1 += row[c + 32]; s2 += row[c + 64]; s3 += row[c + 96]; }
+    for (; c < c1; c += 32) s0 += row[c];
+    const double sum = warp_sum((s0 + s1) + (s2 + s3));
+    if (lane == 0) out[r] = sum;
+}
+
+void launch_rowsum(const LaunchCtx &c, const int *ids, int nfb, int j, int max_cols) {
+    dim3 grid((max_cols + RS_CHUNK - 1) / RS_CHUNK, nfb, c.nbatch);
+    rowsum_kernel<<<grid, 1024, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.rsbuf, c.maxfb, c.maxchunks);
+}
+
+// =====================================================================================================
+// panel kernel: one CTA (1024 threads, thread (u,q) owns T[u][q] and G[u][q] in registers) per front and network.
 //   s_u  = sum_{v >= je} P[j+u, v]                (mass leaving the panel; GTH row sums)
-//   W    = (I - P_XX)^-1 by subtraction-free Gauss-Jordan; pivot d_p = sum_{q != p} T[p,q] + s_p
+//   W    = (I - P_XX)^-1 by subtraction-free Gauss-Jordan; pivot d_p = sum_{q != p} T[p,q] + s_p.
+// Row p is published to shared memory (double buffered) by its own warp one step ahead, together with 1/d_p,
+// so a step costs one barrier, one shuffle and three FMAs for everybody else.
+// Fronts with few columns also apply W to their row panel here (U' = W [P_XR | tau_X]).
 // =====================================================================================================
 __global__ void __launch_bounds__(1024, 1)
 panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j,
-             double *wbuf, int maxfb, int *errflag) {
+             double *wbuf, const double *rsbuf, int maxfb, int maxchunks, int *errflag) {
     const DFront F = fronts[ids[blockIdx.x]];
     if (j >= F.k) return;
     double *M = pool + (long long)blockIdx.y * pool_stride + F.off;
@@ -30,57 +66,110 @@ panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const in
     const int je = j + nbp;
     const int u = threadIdx.x >> 5, q = threadIdx.x & 31;
 
-    __shared__ double Ts[NB_INNER][NB_INNER + 1];
-    __shared__ double Gs[NB_INNER][NB_INNER + 1];
-    __shared__ double Ss[NB_INNER];
+    __shared__ double rowT[2][NB_INNER];
+    __shared__ double rowG[2][NB_INNER];
+    __shared__ double rowS[2], rowRD[2];
     __shared__ double Ds[NB_INNER];
+    __shared__ double Ws[NB_INNER][NB_INNER];
+    __shared__ double xs[NB_INNER][128];
 
     // row sums over everything to the right of the panel (tau column excluded)
-    double s = 0.0;
+    double s = 1.0;   // padding rows behave like isolated absorbing nodes
     if (u < nbp) {
-        const double *row = M + (long long)(j + u) * F.ld;
-        for (int c = je + q; c < F.f; c += 32) s += row[c];
-        s = warp_sum(s);
-    } else {
-        s = 1.0;   // padding rows behave like isolated absorbing nodes
+        if (F.f - je > RS_SPLIT) {
+            const int nch = (F.f - je + RS_CHUNK - 1) / RS_CHUNK;
+            const double *rs = rsbuf + (((long long)blockIdx.y * maxfb + blockIdx.x) * maxchunks) * NB_INNER;
+            s = 0.0;
+            for (int ch = q; ch < nch; ch += 32) s += rs[ch * NB_INNER + u];
+            s = warp_sum(s);
+        } else {
+            const double *row = M + (long long)(j + u) * F.ld;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int c = je + q;
+            for (; c + 96 < F.f; c += 128) { s0 += row[c]; s1 += row[c + 32]; s2 += row[c + 64]; s3 += row[c + 96]; }
+            for (; c < F.f; c += 32) s0 += row[c];
+            s = warp_sum((s0 + s1) + (s2 + s3));
+        }
     }
-    if (q == 0) Ss[u] = s;
-    Ts[u][q] = (u < nbp && q < nbp && u != q) ? M[(long long)(j + u) * F.ld + j + q] : 0.0;
-    Gs[u][q] = (u == q) ? 1.0 : 0.0;
-
+    double t = (u < nbp && q < nbp && u != q) ? M[(long long)(j + u) * F.ld + j + q] : 0.0;
+    double g = (u == q) ? 1.0 : 0.0;
+    if (u == 0) {
+        const double d = warp_sum(t) + s;
+        rowT[0][q] = t;
+        rowG[0][q] = g;
+        if (q == 0) {
+            rowS[0] = s;
+            rowRD[0] = 1.0 / d;
+            Ds[0] = d;
+            if (!(d > 0.0) || isinf(d)) atomicOr(errflag, 1);
+        }
+    }
     for (int p = 0; p < nbp; ++p) {
         __syncthreads();
-        const double tp = Ts[p][q];
-        const double gp = Gs[p][q];
-        const double sp = Ss[p];
-        const double d = warp_sum(tp) + sp;
-        if (u == p) {
-            if (q == 0) {
-                Ds[p] = d;
-                if (!(d > 0.0) || isinf(d)) atomicOr(errflag, 1);
+        const int b = p & 1;
+        if (u != p) {
+            const double tp = rowT[b][q], gp = rowG[b][q], sp = rowS[b], rd = rowRD[b];
+            const double tup = __shfl_sync(0xffffffffu, t, p);
+            const double fup = (tup == 0.0) ? 0.0 : tup * rd;   // rows that do not reach p stay clean even if d == 0
+            t = (q == p || q == u) ? 0.0 : fma(fup, tp, t);
+            g = fma(fup, gp, g);
+            s = fma(fup, sp, s);
+            if (u == p + 1 && u < nbp) {          // publish the next pivot row one step ahead
+                const double d = warp_sum(t) + s;
+                rowT[b ^ 1][q] = t;
+                rowG[b ^ 1][q] = g;
+                if (q == 0) {
+                    rowS[b ^ 1] = s;
+                    rowRD[b ^ 1] = 1.0 / d;
+                    Ds[u] = d;
+                    if (!(d > 0.0) || isinf(d)) atomicOr(errflag, 1);
+                }
             }
-        } else {
-            const double fup = Ts[u][p] / d;
-            __syncwarp();
-            double t = Ts[u][q] + fup * tp;
-            if (q == p || q == u) t = 0.0;
-            Ts[u][q] = t;
-            Gs[u][q] += fup * gp;
-            if (q == 0) Ss[u] = Ss[u] + fup * sp;
         }
     }
     __syncthreads();
-    double *W = wbuf + ((long long)blockIdx.y * maxfb + blockIdx.x) * (NB_INNER * NB_INNER);
-    W[u * NB_INNER + q] = Gs[u][q] / Ds[u < nbp ? u : 0] * (u < nbp ? 1.0 : 0.0);
+    const double w = (u < nbp) ? g / Ds[u] : 0.0;
+    Ws[u][q] = w;
+    wbuf[((long long)blockIdx.y * maxfb + blockIdx.x) * (NB_INNER * NB_INNER) + u * NB_INNER + q] = w;
+
+    // fused row panel for narrow fronts: columns je..f (f = tau column) in slabs of 128 staged through smem
+    const int ncols = F.f + 1 - je;
+    if (ncols > FUSE_COLS) return;
+    const int cc = threadIdx.x & 127, r0 = threadIdx.x >> 7;
+    for (int cs = 0; cs < ncols; cs += 128) {
+        __syncthreads();
+        const bool live = cs + cc < ncols;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = r0 + 8 * i;
+            xs[r][cc] = (live && r < nbp) ? M[(long long)(j + r) * F.ld + je + cs + cc] : 0.0;
+        }
+        __syncthreads();
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+        for (int tt = 0; tt < NB_INNER; ++tt) {
+            const double x = xs[tt][cc];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fma(Ws[r0 + 8 * i][tt], x, acc[i]);
+        }
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = r0 + 8 * i;
+                if (r < nbp) M[(long long)(j + r) * F.ld + je + cs + cc] = acc[i];
+            }
+        }
+    }
 }
 
 void launch_panel(const LaunchCtx &c, const int *ids, int nfb, int j) {
     dim3 grid(nfb, c.nbatch);
-    panel_kernel<<<grid, 1024, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.maxfb, c.errflag);
+    panel_kernel<<<grid, 1024, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.rsbuf, c.maxfb,
+                                             c.maxchunks, c.errflag);
 }
 
 // =====================================================================================================
-// row panel: U' = W [P_XR | tau_X] in place, columns je..f (f = tau column)
+// row panel for wide fronts: U' = W [P_XR | tau_X] in place, columns je..f (f = tau column)
 // 256 threads handle 128 columns: thread (h = tid/128, col = tid%128) produces rows 16h..16h+15
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
@@ -90,6 +179,7 @@ rowpanel_kernel(double *pool, long long pool_stride, const DFront *fronts, const
     if (j >= F.k) return;
     const int nbp = min(NB_INNER, F.k - j);
     const int je = j + nbp;
+    if (F.f + 1 - je <= FUSE_COLS) return;       // done inside the panel kernel
     const int col = je + blockIdx.x * 128 + (threadIdx.x & 127);
     if (je + (int)blockIdx.x * 128 > F.f) return;
     double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
@@ -130,13 +220,20 @@ void launch_rowpanel(const LaunchCtx &c, const int *ids, int nfb, int j, int max
 constexpr int FT = 64, FK = 16;
 
 __global__ void __launch_bounds__(256)
-update_dfma_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode) {
+update_dfma_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode_in,
+                   int split) {
     const DFront F = fronts[ids[blockIdx.y]];
     Region R;
+    int mode = mode_in, tile = blockIdx.x;
+    if (mode_in == MODE_AB) {
+        if (tile < split) mode = MODE_A; else { mode = MODE_B; tile -= split; }
+    } else if (mode_in == MODE_D1) {
+        if (tile < split) mode = MODE_D1A; else { mode = MODE_D1B; tile -= split; }
+    }
     if (!get_region(F.f, F.k, j, mode, R)) return;
     const int tiles_c = (R.c1 - R.c0 + FT - 1) / FT;
     const int tiles_r = (R.r1 - R.r0 + FT - 1) / FT;
-    const int tr = blockIdx.x / tiles_c, tc = blockIdx.x % tiles_c;
+    const int tr = tile / tiles_c, tc = tile % tiles_c;
     if (tr >= tiles_r) return;
     double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
     const int rb = R.r0 + tr * FT, cb = R.c0 + tc * FT;
@@ -186,58 +283,106 @@ update_dfma_kernel(double *pool, long long pool_stride, const DFront *fronts, co
 
 // =====================================================================================================
 // Schur update on the FP64 tensor cores: DMMA m8n8k4 (the sm_100a FP64 tensor instruction; tcgen05 has
-// no f64 kind).  CTA tile 128 x 64, 8 warps as 4 (M) x 2 (N), warp tile 32 x 32 = 4 x 4 MMA tiles,
-// K staged through shared memory 32 at a time.  Shared strides 36 / 68 doubles make both fragment loads
-// bank-conflict free (stride = 4 mod 16).
+// no f64 kind).  CTA tile 128 x 64, 8 warps as 4 (M) x 2 (N), warp tile 32 x 32 = 4 x 4 MMA tiles.
+// K is staged 16 at a time through a 3-stage cp.async ring (global -> shared, no register staging); two CTAs
+// are resident per SM so one CTA's prologue / epilogue hides behind the other's DMMAs.  The accumulators start
+// from the C tile itself (loaded while the pipeline fills), so the epilogue is a plain store.
+// Shared strides 20 / 68 doubles make both fragment loads bank-conflict free (stride = 4 mod 16).
 // =====================================================================================================
-constexpr int TM = 128, TN = 64, TK = 32;
+constexpr int TM = 128, TN = 64, TK = 16, TSTG = 3;
 constexpr int AS_LD = TK + 4, BS_LD = TN + 4;
+constexpr int TSTAGE_DOUBLES = TM * AS_LD + TK * BS_LD;
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 8 : 0;   // 0 -> zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(256, 2)
-update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode) {
+update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode_in,
+                   int split) {
     const DFront F = fronts[ids[blockIdx.y]];
     Region R;
+    int mode = mode_in, tile = blockIdx.x;
+    if (mode_in == MODE_AB) {
+        if (tile < split) mode = MODE_A; else { mode = MODE_B; tile -= split; }
+    } else if (mode_in == MODE_D1) {
+        if (tile < split) mode = MODE_D1A; else { mode = MODE_D1B; tile -= split; }
+    }
     if (!get_region(F.f, F.k, j, mode, R)) return;
     const int tiles_c = (R.c1 - R.c0 + TN - 1) / TN;
     const int tiles_r = (R.r1 - R.r0 + TM - 1) / TM;
-    const int tr = blockIdx.x / tiles_c, tc = blockIdx.x % tiles_c;
+    const int tr = tile / tiles_c, tc = tile % tiles_c;
     if (tr >= tiles_r) return;
     double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
     const int rb = R.r0 + tr * TM, cb = R.c0 + tc * TN;
+    const long long ld = F.ld;
 
     extern __shared__ double smem[];
-    double *As = smem;                    // [TM][AS_LD]
-    double *Bs = smem + TM * AS_LD;       // [TK][BS_LD]
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wm = warp & 3, wn = warp >> 2;
     const int g = lane >> 2, t4 = lane & 3;
 
+    // accumulators = C tile (issued first: their latency hides behind the pipeline prologue)
     double acc[4][4][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int mi = 0; mi < 4; ++mi) {
+        const int r = rb + wm * 32 + mi * 8 + g;
+        const double *row = M + (long long)r * ld;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        for (int ni = 0; ni < 4; ++ni) {
+            const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
+            acc[mi][ni][0] = (r < R.r1 && c0 < R.c1) ? row[c0] : 0.0;
+            acc[mi][ni][1] = (r < R.r1 && c0 + 1 < R.c1) ? row[c0 + 1] : 0.0;
+        }
+    }
 
-    for (int kb = R.k0; kb < R.k1; kb += TK) {
-        // A tile: rows rb.., pivots kb..kb+31  (256-byte runs per row)
-#pragma unroll 4
-        for (int i = threadIdx.x; i < TM * TK; i += 256) {
-            const int r = i >> 5, kk = i & 31;
-            As[r * AS_LD + kk] = (rb + r < R.r1 && kb + kk < R.k1) ? M[(long long)(rb + r) * F.ld + kb + kk] : 0.0;
+    const int nk = (R.k1 - R.k0 + TK - 1) / TK;
+    // per-thread load slots: A element (row ar + 16 i, pivot kb + ak), B element (pivot kb + bk + 4 i, column bc)
+    const int ar = threadIdx.x >> 4, ak = threadIdx.x & 15;
+    const int bk = threadIdx.x >> 6, bc = threadIdx.x & 63;
+    const double *pa = M + (long long)(rb + ar) * ld + ak;
+    const double *pb = M + (long long)bk * ld + cb + bc;
+    unsigned amask = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) amask |= (rb + ar + 16 * i < R.r1) ? (1u << i) : 0u;
+    const bool bcol_ok = cb + bc < R.c1;
+    double *sa = smem + ar * AS_LD + ak;
+    double *sb = smem + TM * AS_LD + bk * BS_LD + bc;
+    auto load_stage = [&](int stg, int kb) {
+        const bool ka = kb + ak < R.k1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool ok = ka && ((amask >> i) & 1u);
+            cp_async8(sa + stg * TSTAGE_DOUBLES + i * 16 * AS_LD, ok ? pa + (long long)i * 16 * ld + kb : M, ok);
         }
-        // B tile: pivots kb.., cols cb..cb+63
-#pragma unroll 4
-        for (int i = threadIdx.x; i < TK * TN; i += 256) {
-            const int kk = i >> 6, cc = i & 63;
-            Bs[kk * BS_LD + cc] = (cb + cc < R.c1 && kb + kk < R.k1) ? M[(long long)(kb + kk) * F.ld + cb + cc] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool ok = bcol_ok && (kb + bk + 4 * i < R.k1);
+            cp_async8(sb + stg * TSTAGE_DOUBLES + i * 4 * BS_LD, ok ? pb + (long long)(kb + 4 * i) * ld : M, ok);
         }
+    };
+#pragma unroll
+    for (int st = 0; st < TSTG - 1; ++st) {
+        if (st < nk) load_stage(st, R.k0 + st * TK);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<TSTG - 2>();
         __syncthreads();
+        const int nxt = kt + TSTG - 1;
+        if (nxt < nk) load_stage(nxt % TSTG, R.k0 + nxt * TK);
+        cp_async_commit();
+        const double *As = smem + (kt % TSTG) * TSTAGE_DOUBLES;
+        const double *Bs = As + TM * AS_LD;
 #pragma unroll
         for (int k4 = 0; k4 < TK / 4; ++k4) {
             double a[4], b[4];
@@ -250,39 +395,162 @@ update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, co
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
         }
-        __syncthreads();
     }
-    // epilogue: C += acc.  Thread holds C[g][2*t4 + {0,1}] of every 8 x 8 tile.
+    cp_async_wait<0>();
+    // epilogue: thread holds C[g][2*t4 + {0,1}] of every 8 x 8 tile
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
         const int r = rb + wm * 32 + mi * 8 + g;
         if (r >= R.r1) continue;
-        double *row = M + (long long)r * F.ld;
+        double *row = M + (long long)r * ld;
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
             const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
-            if (c0 < R.c1) row[c0] += acc[mi][ni][0];
-            if (c0 + 1 < R.c1) row[c0 + 1] += acc[mi][ni][1];
+            if (c0 < R.c1) row[c0] = acc[mi][ni][0];
+            if (c0 + 1 < R.c1) row[c0 + 1] = acc[mi][ni][1];
         }
     }
 }
 
-int update_tile_m(int gemm_path) { return gemm_path == 1 ? FT : TM; }
-int update_tile_n(int gemm_path) { return gemm_path == 1 ? FT : TN; }
+// =====================================================================================================
+// Large-region Schur update: CTA tile 128 x 128, 16 warps as 4 (M) x 4 (N), warp tile 32 x 32 = 4 x 4 DMMA tiles,
+// K staged 16 at a time through a 4-stage cp.async ring (global -> shared without touching registers), so loads
+// of stage t+3 overlap the DMMAs of stage t.  The accumulators start from the C tile itself (loaded while the
+// pipeline fills), so the epilogue is a plain store: C = C + A B with no read-modify-write tail.
+// =====================================================================================================
+constexpr int BM = 128, BN = 128, BK = 16, STG = 4;
+constexpr int BA_LD = BK + 4, BB_LD = BN + 4;
+constexpr int STAGE_DOUBLES = BM * BA_LD + BK * BB_LD;
 
-void launch_update(const LaunchCtx &c, const int *ids, int nfb, int j, int mode, int max_tiles) {
+__global__ void __launch_bounds__(512, 1)
+update_dmma_big_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode_in,
+                       int split) {
+    const DFront F = fronts[ids[blockIdx.y]];
+    Region R;
+    int mode = mode_in, tile = blockIdx.x;
+    if (mode_in == MODE_AB) {
+        if (tile < split) mode = MODE_A; else { mode = MODE_B; tile -= split; }
+    } else if (mode_in == MODE_D1) {
+        if (tile < split) mode = MODE_D1A; else { mode = MODE_D1B; tile -= split; }
+    }
+    if (!get_region(F.f, F.k, j, mode, R)) return;
+    const int tiles_c = (R.c1 - R.c0 + BN - 1) / BN;
+    const int tiles_r = (R.r1 - R.r0 + BM - 1) / BM;
+    const int tr = tile / tiles_c, tc = tile % tiles_c;
+    if (tr >= tiles_r) return;
+    double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
+    const int rb = R.r0 + tr * BM, cb = R.c0 + tc * BN;
+    const long long ld = F.ld;
+
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp & 3, wn = warp >> 2;          // 16 warps as 4 (M) x 4 (N), warp tile 32 x 32
+    const int g = lane >> 2, t4 = lane & 3;
+
+    // accumulators = C tile (issued first: their latency hides behind the pipeline prologue)
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        const int r = rb + wm * 32 + mi * 8 + g;
+        const double *row = M + (long long)r * ld;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
+            acc[mi][ni][0] = (r < R.r1 && c0 < R.c1) ? row[c0] : 0.0;
+            acc[mi][ni][1] = (r < R.r1 && c0 + 1 < R.c1) ? row[c0 + 1] : 0.0;
+        }
+    }
+
+    const int nk = (R.k1 - R.k0 + BK - 1) / BK;
+    // per-thread load slots: A element (row ar + 32 i, pivot kb + ak), B element (pivot kb + bk + 4 i, column bc)
+    const int ar = threadIdx.x >> 4, ak = threadIdx.x & 15;
+    const int bk = threadIdx.x >> 7, bc = threadIdx.x & 127;
+    const double *pa = M + (long long)(rb + ar) * ld + ak;
+    const double *pb = M + (long long)bk * ld + cb + bc;
+    unsigned amask = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) amask |= (rb + ar + 32 * i < R.r1) ? (1u << i) : 0u;
+    const bool bcol_ok = cb + bc < R.c1;
+    double *sa = smem + ar * BA_LD + ak;
+    double *sb = smem + BM * BA_LD + bk * BB_LD + bc;
+    auto load_stage = [&](int stg, int kb) {
+        const bool ka = kb + ak < R.k1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool ok = ka && ((amask >> i) & 1u);
+            cp_async8(sa + stg * STAGE_DOUBLES + i * 32 * BA_LD, ok ? pa + (long long)i * 32 * ld + kb : M, ok);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool ok = bcol_ok && (kb + bk + 4 * i < R.k1);
+            cp_async8(sb + stg * STAGE_DOUBLES + i * 4 * BB_LD, ok ? pb + (long long)(kb + 4 * i) * ld : M, ok);
+        }
+    };
+#pragma unroll
+    for (int st = 0; st < STG - 1; ++st) {
+        if (st < nk) load_stage(st, R.k0 + st * BK);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STG - 2>();
+        __syncthreads();
+        const int nxt = kt + STG - 1;
+        if (nxt < nk) load_stage(nxt % STG, R.k0 + nxt * BK);
+        cp_async_commit();
+        const double *As = smem + (kt % STG) * STAGE_DOUBLES;
+        const double *Bs = As + BM * BA_LD;
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 4; ++k4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = As[(wm * 32 + mi * 8 + g) * BA_LD + k4 * 4 + t4];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(k4 * 4 + t4) * BB_LD + wn * 32 + ni * 8 + g];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        const int r = rb + wm * 32 + mi * 8 + g;
+        if (r >= R.r1) continue;
+        double *row = M + (long long)r * ld;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
+            if (c0 < R.c1) row[c0] = acc[mi][ni][0];
+            if (c0 + 1 < R.c1) row[c0 + 1] = acc[mi][ni][1];
+        }
+    }
+}
+
+int update_tile_m(int gemm_path) { return gemm_path == 1 ? FT : (gemm_path == 2 ? BM : TM); }
+int update_tile_n(int gemm_path) { return gemm_path == 1 ? FT : (gemm_path == 2 ? BN : TN); }
+
+void launch_update(const LaunchCtx &c, const int *ids, int nfb, int j, int mode, int max_tiles, int split) {
     if (max_tiles <= 0) return;
     dim3 grid(max_tiles, nfb, c.nbatch);
     if (c.gemm_path == 1) {
-        update_dfma_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode);
+        update_dfma_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split);
+    } else if (c.gemm_path == 2) {
+        static bool big_attr_set = false;
+        const size_t smem = (size_t)STG * STAGE_DOUBLES * sizeof(double);
+        if (!big_attr_set) {
+            cudaFuncSetAttribute(update_dmma_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            big_attr_set = true;
+        }
+        update_dmma_big_kernel<<<grid, 512, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split);
     } else {
         static bool attr_set = false;
-        const size_t smem = (size_t)(TM * AS_LD + TK * BS_LD) * sizeof(double);
+        const size_t smem = (size_t)TSTG * TSTAGE_DOUBLES * sizeof(double);
         if (!attr_set) {
             cudaFuncSetAttribute(update_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_set = true;
         }
-        update_dmma_kernel<<<grid, 256, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode);
+        update_dmma_kernel<<<grid, 256, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split);
     }
 }
 

@@ -20,8 +20,14 @@
 
 namespace ngt {
 
-constexpr int NB_INNER = 32;    // pivots per panel (in-SM Gauss-Jordan block)
-constexpr int NB_OUTER = 128;   // pivots per delayed trailing update (K of the big Schur GEMM)
+#ifndef NGT_NB_OUTER
+#define NGT_NB_OUTER 256
+#endif
+#ifndef NGT_FUSE_COLS
+#define NGT_FUSE_COLS 384
+#endif
+constexpr int NB_INNER = 32;             // pivots per panel (in-SM Gauss-Jordan block)
+constexpr int NB_OUTER = NGT_NB_OUTER;   // pivots per delayed trailing update (K of the big Schur GEMM)
 
 struct DFront {
     long long off;   // offset in the pool (doubles)
@@ -29,7 +35,15 @@ struct DFront {
     int parent;      // front id or -1
 };
 
-enum UpdateMode { MODE_A = 0, MODE_B = 1, MODE_D = 2 };
+constexpr int RS_CHUNK = 512;   // columns per partial-row-sum CTA (one warp per panel row)
+constexpr int RS_SPLIT = 4096;  // fronts with more columns right of the panel get multi-CTA row sums
+constexpr int FUSE_COLS = NGT_FUSE_COLS; // fronts with at most this many columns apply W to their row panel inside the panel kernel
+
+// Schur-update regions.  A/B: L-shaped strips inside an outer block (K = one panel).  D: the delayed trailing update
+// (K = the whole outer block), split for look-ahead into D1 = the strips the NEXT outer block's panels need
+// (D1A column strip, D1B row strip) and D2 = the rest, which may run on a second stream while the next panels run.
+// AB and D1 are "merged" launch modes: CTAs [0, split) take the first region, the others the second.
+enum UpdateMode { MODE_A = 0, MODE_B = 1, MODE_D = 2, MODE_AB = 3, MODE_D1A = 4, MODE_D1B = 5, MODE_D2 = 6, MODE_D1 = 7 };
 
 struct Region { int r0, r1, c0, c1, k0, k1; };
 
@@ -46,8 +60,13 @@ __host__ __device__ inline bool get_region(int f, int k, int j, int mode, Region
     if (mode == MODE_A) { R.r0 = je; R.r1 = f; R.c0 = je; R.c1 = JE; R.k0 = j; R.k1 = je; }
     else if (mode == MODE_B) { R.r0 = je; R.r1 = JE; R.c0 = JE; R.c1 = f + 1; R.k0 = j; R.k1 = je; }
     else {
-        if (je != JE) return false;   // the delayed update runs once, after the last panel of the outer block
-        R.r0 = JE; R.r1 = f; R.c0 = JE; R.c1 = f + 1; R.k0 = J; R.k1 = JE;
+        if (je != JE) return false;   // delayed updates run once, after the last panel of the outer block
+        const int JE2 = (JE + NB_OUTER < k ? JE + NB_OUTER : k);
+        R.k0 = J; R.k1 = JE;
+        if (mode == MODE_D) { R.r0 = JE; R.r1 = f; R.c0 = JE; R.c1 = f + 1; }
+        else if (mode == MODE_D1A) { R.r0 = JE; R.r1 = f; R.c0 = JE; R.c1 = JE2; }
+        else if (mode == MODE_D1B) { R.r0 = JE; R.r1 = JE2; R.c0 = JE2; R.c1 = f + 1; }
+        else { R.r0 = JE2; R.r1 = f; R.c0 = JE2; R.c1 = f + 1; }
     }
     return R.r1 > R.r0 && R.c1 > R.c0;
 }
@@ -60,16 +79,20 @@ struct LaunchCtx {
     const DFront *fronts;     // device array of all fronts
     double *wbuf;             // nbatch * maxfb * NB_INNER*NB_INNER
     int maxfb;                // fronts per batch upper bound (stride of wbuf)
+    double *rsbuf;            // nbatch * maxfb * maxchunks * NB_INNER partial row sums (wide fronts)
+    int maxchunks;
     int *errflag;             // device int
     cudaStream_t stream;
     int gemm_path;            // 0 DMMA, 1 DFMA
 };
 
 // ids: device array of front ids in this batch (nfb of them).
+void launch_rowsum(const LaunchCtx &c, const int *ids, int nfb, int j, int max_cols);
 void launch_panel(const LaunchCtx &c, const int *ids, int nfb, int j);
 void launch_rowpanel(const LaunchCtx &c, const int *ids, int nfb, int j, int max_cols);
 // max_tiles: upper bound of tiles over the fronts of the batch for this (j, mode); computed by the host.
-void launch_update(const LaunchCtx &c, const int *ids, int nfb, int j, int mode, int max_tiles);
+// mode MODE_AB runs both L-shaped regions in one launch: CTAs [0, split) do MODE_A, the rest MODE_B
+void launch_update(const LaunchCtx &c, const int *ids, int nfb, int j, int mode, int max_tiles, int split);
 
 // tile geometry used by the host to size grids
 int update_tile_m(int gemm_path);

@@ -2,7 +2,12 @@
 #include "symbolic.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 
 namespace ngt {
@@ -23,15 +28,19 @@ void build_adjacency(int64_t n, int64_t nnz, const int64_t *src, const int64_t *
         tmp[fill[src[e]]++] = (int32_t)dst[e];
         tmp[fill[dst[e]]++] = (int32_t)src[e];
     }
-    // sort + dedupe each row, compact
+    // dedupe each row with a marker array (order inside a row is irrelevant), compact in place
     std::vector<int64_t> nptr(n + 1, 0);
+    std::vector<int32_t> seen(n, -1);
     int64_t w = 0;
     for (int64_t i = 0; i < n; ++i) {
-        int32_t *b = tmp.data() + g.ptr[i], *e = tmp.data() + g.ptr[i + 1];
-        std::sort(b, e);
-        e = std::unique(b, e);
+        const int64_t b = g.ptr[i], e = g.ptr[i + 1];
         nptr[i] = w;
-        for (int32_t *q = b; q != e; ++q) tmp[w++] = *q;   // w <= read cursor, safe in place
+        for (int64_t q = b; q < e; ++q) {
+            const int32_t v = tmp[q];
+            if (seen[v] == (int32_t)i) continue;
+            seen[v] = (int32_t)i;
+            tmp[w++] = v;   // w <= q, safe in place
+        }
     }
     nptr[n] = w;
     tmp.resize(w);
@@ -43,135 +52,200 @@ namespace {
 
 // ---------------------------------------------------------------------------------------------
 // Nested dissection by BFS level structures (George's automatic nested dissection) on the graph
-// induced on the intermediate nodes.  Emits nodes in elimination order and the supernode boundaries.
+// induced on the intermediate nodes.  Emits nodes in elimination order and the supernode sizes.
 // ---------------------------------------------------------------------------------------------
+// A subgraph in its own compact index space: local ids 0..n-1, `glob` maps back to node ids.  Every recursion
+// level relabels its two halves in BFS order into fresh subgraphs, so sweeps run over contiguous memory and
+// concurrent branches share no cache lines.
+struct Sub {
+    int32_t n = 0;
+    std::vector<int32_t> ptr;    // n + 1
+    std::vector<int32_t> adj;    // local ids
+    std::vector<int32_t> glob;   // local -> node id
+};
+
 struct Dissector {
-    const Adjacency &g;
     int leaf;
-    std::vector<int32_t> tag;      // tag[v] == cur  <=> v belongs to the subset being processed
-    std::vector<int32_t> lvl;      // BFS level scratch
-    std::vector<int32_t> comp;     // component label scratch
-    int32_t next_tag = 1;
-    std::vector<int32_t> order;    // output: node ids in elimination order
-    std::vector<int32_t> sn_start; // output: start position of each supernode
+    int max_par_depth;
+    double min_bal = 0.25;   // smaller side of a split should hold at least this fraction
 
-    Dissector(const Adjacency &g_, int leaf_) : g(g_), leaf(leaf_), tag(g_.n, 0), lvl(g_.n, -1), comp(g_.n, -1) {}
+    // result of dissecting one subset: nodes in elimination order + supernode sizes
+    struct Out {
+        std::vector<int32_t> order;
+        std::vector<int32_t> sn_size;
+        void emit_glob(const Sub &G, const std::vector<int32_t> &locals) {
+            if (locals.empty()) return;
+            sn_size.push_back((int32_t)locals.size());
+            for (int32_t v : locals) order.push_back(G.glob[v]);
+        }
+        void emit_all(const Sub &G) {
+            if (G.n == 0) return;
+            sn_size.push_back(G.n);
+            order.insert(order.end(), G.glob.begin(), G.glob.end());
+        }
+        void append(Out &o) {
+            order.insert(order.end(), o.order.begin(), o.order.end());
+            sn_size.insert(sn_size.end(), o.sn_size.begin(), o.sn_size.end());
+        }
+    };
 
-    void emit(const std::vector<int32_t> &nodes) {
-        if (nodes.empty()) return;
-        sn_start.push_back((int32_t)order.size());
-        order.insert(order.end(), nodes.begin(), nodes.end());
+    explicit Dissector(int leaf_) : leaf(leaf_) {
+        unsigned hw = std::thread::hardware_concurrency();
+        max_par_depth = hw >= 16 ? 4 : hw >= 8 ? 3 : hw >= 4 ? 2 : hw >= 2 ? 1 : 0;
+        if (const char *e = std::getenv("NGT_B200_ND_THREADS_DEPTH")) max_par_depth = std::atoi(e);
+        if (const char *e = std::getenv("NGT_B200_ND_BALANCE")) min_bal = std::atof(e);
     }
 
-    // BFS inside the tagged subset from `start`; fills lvl[] for reached nodes, returns them in visit order.
-    void bfs(int32_t start, int32_t t, std::vector<int32_t> &visit, int32_t &nlev) {
-        visit.clear();
+    // BFS from `start` over unvisited nodes (lvl < 0); appends to `visit`
+    static void bfs(const Sub &G, int32_t start, std::vector<int32_t> &lvl, std::vector<int32_t> &visit, int32_t &nlev) {
+        size_t head = visit.size();
         visit.push_back(start);
         lvl[start] = 0;
-        size_t head = 0;
         nlev = 1;
         while (head < visit.size()) {
-            int32_t u = visit[head++];
-            for (int64_t e = g.ptr[u]; e < g.ptr[u + 1]; ++e) {
-                int32_t v = g.adj[e];
-                if (tag[v] != t || lvl[v] >= 0) continue;
-                lvl[v] = lvl[u] + 1;
-                nlev = lvl[v] + 1;
+            const int32_t u = visit[head++];
+            const int32_t lu = lvl[u] + 1;
+            for (int32_t e = G.ptr[u]; e < G.ptr[u + 1]; ++e) {
+                const int32_t v = G.adj[e];
+                if (lvl[v] >= 0) continue;
+                lvl[v] = lu;
+                nlev = lu + 1;
                 visit.push_back(v);
             }
         }
     }
 
-    void dissect(std::vector<int32_t> &S) {
-        if (S.empty()) return;
-        if ((int)S.size() <= leaf) { emit(S); return; }
-        const int32_t t = next_tag++;
-        for (int32_t v : S) { tag[v] = t; lvl[v] = -1; }
-
-        // ---- connected components of the subset
-        std::vector<std::vector<int32_t> > comps;
-        {
-            std::vector<int32_t> visit;
-            int32_t nlev;
-            for (int32_t v : S) {
-                if (lvl[v] >= 0) continue;
-                bfs(v, t, visit, nlev);
-                comps.push_back(visit);
+    // induced subgraph on `members` (listed in the order that becomes the new local numbering)
+    static void induce(const Sub &G, const std::vector<int32_t> &members, std::vector<int32_t> &newid, Sub &H) {
+        H.n = (int32_t)members.size();
+        H.glob.resize(H.n);
+        H.ptr.assign(H.n + 1, 0);
+        for (int32_t i = 0; i < H.n; ++i) newid[members[i]] = i;
+        size_t cap = 0;
+        for (int32_t v : members) cap += (size_t)(G.ptr[v + 1] - G.ptr[v]);
+        H.adj.clear();
+        H.adj.reserve(cap);
+        for (int32_t i = 0; i < H.n; ++i) {
+            const int32_t v = members[i];
+            H.glob[i] = G.glob[v];
+            for (int32_t e = G.ptr[v]; e < G.ptr[v + 1]; ++e) {
+                const int32_t w = newid[G.adj[e]];
+                if (w >= 0) H.adj.push_back(w);
             }
+            H.ptr[i + 1] = (int32_t)H.adj.size();
         }
-        if (comps.size() > 1) {
-            // large components are dissected on their own; small ones are packed into leaf-sized bins
-            std::vector<int32_t> bin;
-            for (auto &c : comps) {
-                if ((int)c.size() > leaf) continue;
-                if ((int)(bin.size() + c.size()) > leaf) { emit(bin); bin.clear(); }
-                bin.insert(bin.end(), c.begin(), c.end());
+        for (int32_t v : members) newid[v] = -1;
+    }
+
+    void dissect(Sub &G, Out &out, int depth) {
+        if (G.n == 0) return;
+        if (G.n <= leaf) { out.emit_all(G); return; }
+        std::vector<int32_t> lvl(G.n, -1), visit;
+        visit.reserve(G.n);
+        int32_t nlev = 0;
+
+        // ---- first sweep: connectivity + a far node
+        bfs(G, 0, lvl, visit, nlev);
+        if ((int32_t)visit.size() != G.n) {
+            // several components: small ones are packed into leaf-sized bins, large ones dissected on their own
+            std::vector<int32_t> comp_start{0};
+            comp_start.push_back((int32_t)visit.size());
+            for (int32_t v = 0; v < G.n; ++v) {
+                if (lvl[v] >= 0) continue;
+                int32_t nl;
+                bfs(G, v, lvl, visit, nl);
+                comp_start.push_back((int32_t)visit.size());
             }
-            emit(bin);
-            for (auto &c : comps)
-                if ((int)c.size() > leaf) dissect(c);
+            std::vector<int32_t> bin, newid(G.n, -1);
+            std::vector<Sub> big;
+            for (size_t c = 0; c + 1 < comp_start.size(); ++c) {
+                std::vector<int32_t> mem(visit.begin() + comp_start[c], visit.begin() + comp_start[c + 1]);
+                if ((int)mem.size() > leaf) {
+                    big.emplace_back();
+                    induce(G, mem, newid, big.back());
+                } else {
+                    if ((int)(bin.size() + mem.size()) > leaf) { out.emit_glob(G, bin); bin.clear(); }
+                    bin.insert(bin.end(), mem.begin(), mem.end());
+                }
+            }
+            out.emit_glob(G, bin);
+            G = Sub();
+            for (auto &H : big) dissect(H, out, depth);
             return;
         }
-        S.swap(comps[0]);   // same set, BFS order
-        comps.clear();
-
-        // ---- pseudo-peripheral start node: repeat BFS from a min-degree node of the last level
-        std::vector<int32_t> visit;
-        int32_t nlev = 0, start = S[0];
-        for (int it = 0; it < 3; ++it) {
-            for (int32_t v : S) lvl[v] = -1;
-            bfs(start, t, visit, nlev);
+        // ---- second sweep from a min-degree node of the last level (pseudo-peripheral, George & Liu)
+        {
             int32_t best = visit.back();
-            int64_t bestdeg = g.ptr[best + 1] - g.ptr[best];
+            int32_t bestdeg = G.ptr[best + 1] - G.ptr[best];
             for (size_t i = visit.size(); i-- > 0;) {
-                int32_t v = visit[i];
+                const int32_t v = visit[i];
                 if (lvl[v] != nlev - 1) break;
-                int64_t d = g.ptr[v + 1] - g.ptr[v];
+                const int32_t d = G.ptr[v + 1] - G.ptr[v];
                 if (d < bestdeg) { bestdeg = d; best = v; }
             }
-            if (it == 2 || best == start) break;
-            start = best;
+            if (best != 0) {
+                std::fill(lvl.begin(), lvl.end(), -1);
+                visit.clear();
+                bfs(G, best, lvl, visit, nlev);
+            }
         }
-        if (nlev < 3) { emit(S); return; }   // no separator exists (e.g. a clique): one dense supernode
+        if (nlev < 3) { out.emit_all(G); return; }   // no separator exists (e.g. a clique): one dense supernode
 
-        // ---- choose the separator level: smallest level with both sides >= 25 % if possible
+        // ---- choose the separator level: smallest level, imbalance penalised
         std::vector<int64_t> cnt(nlev, 0);
-        for (int32_t v : S) cnt[lvl[v]]++;
+        for (int32_t v = 0; v < G.n; ++v) cnt[lvl[v]]++;
         std::vector<int64_t> before(nlev + 1, 0);
         for (int i = 0; i < nlev; ++i) before[i + 1] = before[i] + cnt[i];
-        const int64_t tot = (int64_t)S.size();
+        const int64_t tot = G.n;
         int bestl = -1;
         double bestcost = 1e300;
         for (int l = 1; l <= nlev - 2; ++l) {
-            int64_t a = before[l], b = tot - before[l + 1];
-            int64_t mn = std::min(a, b);
+            const int64_t a = before[l], b = tot - before[l + 1];
+            const int64_t mn = std::min(a, b);
             if (mn <= 0) continue;
-            // separator size, penalised by imbalance
-            double bal = (double)mn / (double)tot;
-            double cost = (double)cnt[l] * (bal >= 0.25 ? 1.0 : (0.25 / bal) * (0.25 / bal));
+            const double bal = (double)mn / (double)tot;
+            const double cost = (double)cnt[l] * (bal >= min_bal ? 1.0 : (min_bal / bal) * (min_bal / bal));
             if (cost < bestcost) { bestcost = cost; bestl = l; }
         }
-        if (bestl < 0 || cnt[bestl] * 10 > tot * 6) { emit(S); return; }
+        if (bestl < 0 || cnt[bestl] * 10 > tot * 6) { out.emit_all(G); return; }
 
-        // ---- split; trim separator nodes that do not touch the far side
+        // ---- split in BFS order; separator nodes that do not touch the far side join the near side
         std::vector<int32_t> P1, P2, sep;
-        for (int32_t v : S) {
+        for (int32_t v : visit) {
             if (lvl[v] < bestl) P1.push_back(v);
             else if (lvl[v] > bestl) P2.push_back(v);
             else {
                 bool far = false;
-                for (int64_t e = g.ptr[v]; e < g.ptr[v + 1] && !far; ++e) {
-                    int32_t w = g.adj[e];
-                    if (tag[w] == t && lvl[w] == bestl + 1) far = true;
-                }
+                for (int32_t e = G.ptr[v]; e < G.ptr[v + 1] && !far; ++e)
+                    if (lvl[G.adj[e]] == bestl + 1) far = true;
                 if (far) sep.push_back(v); else P1.push_back(v);
             }
         }
-        S.clear();
-        S.shrink_to_fit();
-        dissect(P1);
-        dissect(P2);
-        emit(sep);
+        Sub H1, H2;
+        {
+            std::vector<int32_t> newid(G.n, -1);
+            induce(G, P1, newid, H1);
+            induce(G, P2, newid, H2);
+        }
+        std::vector<int32_t> sep_glob(sep.size());
+        for (size_t i = 0; i < sep.size(); ++i) sep_glob[i] = G.glob[sep[i]];
+        G = Sub();                       // release this level before descending
+        std::vector<int32_t>().swap(lvl);
+        std::vector<int32_t>().swap(visit);
+        if (depth < max_par_depth && H1.n > 4096 && H2.n > 4096) {
+            Out o2;
+            std::thread th([&] { dissect(H2, o2, depth + 1); });
+            dissect(H1, out, depth + 1);
+            th.join();
+            out.append(o2);
+        } else {
+            dissect(H1, out, depth + 1);
+            dissect(H2, out, depth + 1);
+        }
+        if (!sep_glob.empty()) {
+            out.sn_size.push_back((int32_t)sep_glob.size());
+            out.order.insert(out.order.end(), sep_glob.begin(), sep_glob.end());
+        }
     }
 };
 
@@ -329,30 +403,57 @@ void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
     for (int64_t u = 0; u < n; ++u)
         if (present[u] && !kept[u]) inter.push_back((int32_t)u);
     S.nI = (int64_t)inter.size();
-    Dissector D(g, leaf_size > 0 ? leaf_size : 64);
-    // the dissector must not walk through A ∪ B or absent nodes: they never carry the current tag
-    D.order.reserve(inter.size());
-    D.dissect(inter);
-    if ((int64_t)D.order.size() != S.nI) throw std::logic_error("symbolic: ordering lost nodes");
+    Timer tm;
+    Dissector D(leaf_size > 0 ? leaf_size : 64);
+    // top-level subgraph: the rate graph induced on the intermediates (A ∪ B and absent nodes are left out, so
+    // the dissector never walks through them)
+    Sub top;
+    {
+        std::vector<int32_t> newid(n, -1);
+        top.n = (int32_t)inter.size();
+        top.glob = inter;
+        for (int32_t i = 0; i < top.n; ++i) newid[inter[i]] = i;
+        top.ptr.assign(top.n + 1, 0);
+        top.adj.reserve(g.adj.size());
+        for (int32_t i = 0; i < top.n; ++i) {
+            const int32_t u = inter[i];
+            for (int64_t e = g.ptr[u]; e < g.ptr[u + 1]; ++e) {
+                const int32_t w = newid[g.adj[e]];
+                if (w >= 0) top.adj.push_back(w);
+            }
+            top.ptr[i + 1] = (int32_t)top.adj.size();
+        }
+    }
+    tm.lap("top-level subgraph");
+    Dissector::Out ord;
+    ord.order.reserve(inter.size());
+    D.dissect(top, ord, 0);
+    if ((int64_t)ord.order.size() != S.nI) throw std::logic_error("symbolic: ordering lost nodes");
+    std::vector<int32_t> sn_start;
+    {
+        int32_t acc = 0;
+        for (int32_t z : ord.sn_size) { sn_start.push_back(acc); acc += z; }
+    }
+    tm.lap("nested dissection");
 
     const int64_t npos = S.nI + S.nA + S.nB;
     S.pos.assign(n, -1);
     S.node_at.assign(npos, -1);
-    for (int64_t p = 0; p < S.nI; ++p) { S.pos[D.order[p]] = (int32_t)p; S.node_at[p] = D.order[p]; }
+    for (int64_t p = 0; p < S.nI; ++p) { S.pos[ord.order[p]] = (int32_t)p; S.node_at[p] = ord.order[p]; }
     assign_kept_positions(A, B, S);
 
     // ---- supernodal symbolic factorisation
-    const int32_t ns = (int32_t)D.sn_start.size();
-    D.sn_start.push_back((int32_t)S.nI);
+    const int32_t ns = (int32_t)sn_start.size();
+    sn_start.push_back((int32_t)S.nI);
     S.pos_front.assign(npos, -1);
     S.fronts.resize(ns + 1);
     std::vector<int32_t> mark(npos, -1);
     std::vector<std::vector<int32_t> > kids(ns + 1);
     std::vector<std::vector<int32_t> > upd(ns);   // update sets (freed into fidx at the end)
     for (int32_t s = 0; s < ns; ++s)
-        for (int32_t p = D.sn_start[s]; p < D.sn_start[s + 1]; ++p) S.pos_front[p] = s;
+        for (int32_t p = sn_start[s]; p < sn_start[s + 1]; ++p) S.pos_front[p] = s;
     for (int32_t s = 0; s < ns; ++s) {
-        const int32_t first = D.sn_start[s], last = D.sn_start[s + 1];
+        const int32_t first = sn_start[s], last = sn_start[s + 1];
         std::vector<int32_t> &U = upd[s];
         for (int32_t p = first; p < last; ++p) {
             const int32_t u = S.node_at[p];
@@ -374,6 +475,7 @@ void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
         else F.parent = S.pos_front[U[0]];
         if (F.parent >= 0) kids[F.parent].push_back(s);
     }
+    tm.lap("supernodal symbolic");
     // root
     {
         Front &R = S.fronts[ns];
@@ -399,6 +501,7 @@ void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
     S.fronts[ns].idx_off = (int64_t)S.fidx.size();
     for (int64_t p = S.nI; p < npos; ++p) S.fidx.push_back((int32_t)p);
     finish_layout(S);
+    tm.lap("layout, maps, batches");
 }
 
 }  // namespace ngt

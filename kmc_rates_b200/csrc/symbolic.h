@@ -11,11 +11,27 @@
 //     batches of fronts that are eliminated by the same kernel launches.
 // No arithmetic happens here; the numeric phase never allocates.
 #pragma once
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include <string>
 
 namespace ngt {
+
+// section timer, printed to stderr when NGT_B200_TIMING is set
+struct Timer {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    Timer() : on(std::getenv("NGT_B200_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void lap(const char *what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[ngt timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
 
 struct Front {
     int32_t k;        // pivots eliminated in this front

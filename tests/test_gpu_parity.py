@@ -26,7 +26,7 @@ def _dense_K(n, src, dst, k):
     return K
 
 
-@pytest.mark.parametrize("gemm_path", [0, 1], ids=["dmma", "dfma"])
+@pytest.mark.parametrize("gemm_path", [0, 1, 2], ids=["dmma", "dfma", "dmma128"])
 @pytest.mark.parametrize("case", CASES, ids=IDS)
 def test_sparse_path_matches_reference_golden(case, gemm_path):
     from kmc_rates_b200 import NGT
@@ -71,7 +71,7 @@ def test_committors_match_reference_golden(case):
 DENSE = [c for c in CASES if c["gen"] in ("complete_deterministic", "complete_random")]
 
 
-@pytest.mark.parametrize("gemm_path", [0, 1], ids=["dmma", "dfma"])
+@pytest.mark.parametrize("gemm_path", [0, 1, 2], ids=["dmma", "dfma", "dmma128"])
 @pytest.mark.parametrize("case", DENSE, ids=[c["name"] for c in DENSE])
 def test_dense_path_matches_reference_golden(case, gemm_path):
     from kmc_rates_b200 import NGT
