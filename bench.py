@@ -35,7 +35,18 @@ METRIC = "NGT nodes eliminated/s"
 UNIT = "nodes/s"
 SIDE = 316            # 316^2 = 99 856 minima, ~9.9e5 transition states
 TEMPERATURE = 0.3
-CPU_SAMPLE_SIDE = 50  # reference CPU NGT on a 2 500-minima landscape of the same generator: ~5 s per network per core
+CPU_SAMPLE_SIDE = 70  # cpu_baseline leg: reference CPU NGT on 4 900-minima landscapes, ~20 s per network per core
+REF_BUDGET_S = 240.0  # --impl reference: total wall-clock budget; the sample size per step is derived from it
+# Measured on this pool's host cores: the reference takes ~3.1 s at 2 500 minima and grows ~ n^2.1
+# (4.8 s -> 87 s from 2 500 to 10 000 minima); used only to size the bounded sample.
+REF_T0_S, REF_N0, REF_EXP = 3.1, 2500.0, 2.1
+
+
+def reference_sample_side(steps, warmup):
+    """largest landscape side whose estimated reference time fits REF_BUDGET_S over steps+warmup steps (>= 50)"""
+    per_step = REF_BUDGET_S / max(1, steps + warmup)
+    n = REF_N0 * (per_step / REF_T0_S) ** (1.0 / REF_EXP)
+    return int(max(50, min(100, n ** 0.5)))
 
 
 def workload_config(n_gpus, side):
@@ -138,10 +149,12 @@ def cpu_baseline_object(cores=None, side=CPU_SAMPLE_SIDE):
     nodes, solve, wall = cpu_reference_step(side, cores, kind)
     return {"value": nodes / solve, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": "%d independent %d-minima landscapes of the same generator (one per host core, concurrently); "
-                      "compute_rates() of the %s timed per worker (steady clock), slowest worker %.2f s"
+                      "compute_rates() of the %s timed per worker (steady clock), slowest worker %.2f s. Bounded sample: "
+                      "the reference's cost grows ~n^2.1 (BASELINE.md), so at the full 99 856-minima size it would be "
+                      "~%.0fx slower per node than measured here"
                       % (cores, side * side, "reference C++ NGT compiled from /root/reference (oracle/_ref)"
-                         if kind == "reference" else "oracle C++ port", solve),
-            "single_core_value": None}
+                         if kind == "reference" else "oracle C++ port", solve, (99856.0 / (side * side)) ** 1.1),
+            "extrapolated_full_size_value": nodes / solve / (99856.0 / (side * side)) ** 1.1}
 
 
 def run_reference(args):
@@ -151,7 +164,7 @@ def run_reference(args):
     from oracle import cpu_ngt
     kind = cpu_ngt.best_kind()
     cores = os.cpu_count() or 1
-    side = CPU_SAMPLE_SIDE if (args.steps + args.warmup) <= 30 else 36
+    side = reference_sample_side(args.steps, args.warmup)
     for _ in range(args.warmup):
         cpu_reference_step(side, cores, kind)
     tot_nodes, tot_t = 0, 0.0
@@ -160,9 +173,12 @@ def run_reference(args):
         tot_nodes += nodes
         tot_t += solve
     value = tot_nodes / tot_t
-    sample = ("each step: %d independent %d-minima landscapes (same generator as the GPU arm, bounded size), one per "
-              "host core concurrently, compute_rates() of the %s" %
-              (cores, side * side, "unmodified reference C++ NGT (oracle/_ref)" if kind == "reference" else "oracle C++ port"))
+    sample = ("each step: %d independent %d-minima landscapes (same generator as the GPU arm, bounded so that "
+              "steps+warmup fit ~%d s), one per host core concurrently, compute_rates() of the %s; the reference's cost "
+              "grows ~n^2.1, so this bounded sample overstates its full-size (99 856 minima) rate by ~%.0fx" %
+              (cores, side * side, int(REF_BUDGET_S),
+               "unmodified reference C++ NGT (oracle/_ref)" if kind == "reference" else "oracle C++ port",
+               (99856.0 / (side * side)) ** 1.1))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
@@ -277,8 +293,11 @@ def main():
     barrier()
     ms_total = h.timed_steps(args.steps)
     barrier()
-    st = h.stats()
     rates = h.rates()
+    # per-phase breakdown from one extra step outside the CUDA graph (events between the phases), not timed above
+    h.phase_one()
+    h.phase_two()
+    st = h.stats()
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -330,7 +349,7 @@ def main():
             pass
         dgemm = measure_dgemm_peak(torch)
         pms, pfl, pl = h.profile_schur()
-        step_ms_single = h.timed_steps(1)
+        step_ms_single = h.stats()["ms_profiled_pass"]   # the same profiled pass: consistent event overheads
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "schur_dram_bytes_per_launch.json")
         if os.path.exists(tpath):
@@ -346,6 +365,9 @@ def main():
                            "MEASURED_PEAKS.json carries no FP64 figure (hbm_gbs=%s)" % peaks.get("hbm_gbs"),
             "flops_per_step": pfl, "launches_per_step": pl, "kernel_ms_per_step": pms,
             "share_of_step": pms / step_ms_single,
+            "share_note": "kernel CUDA-event time / duration of the same profiled (event-bracketed, graph-free) pass; "
+                          "ncu launch list of the same step: profiles/r01_launches_c2.md (panel_kernel, latency-bound "
+                          "32x32 Gauss-Jordan, is co-dominant there)",
             "hbm_model": {
                 "note": "SURVEY §8(d) sparse-phase model: bytes a one-node-at-a-time elimination would stream",
                 "alg_bytes_per_step": st["alg_bytes"], "achieved_GBs": st["alg_bytes"] / (ms_per_step * 1e-3) / 1e9,
@@ -379,7 +401,8 @@ def main():
             "stats": {"nodes_eliminated_per_step": nodes_per_step, "rates": nnz, "fronts": st["n_fronts"],
                       "levels": st["n_levels"], "max_front": st["max_front"], "pool_GB": st["pool_doubles"] * 8 / 1e9,
                       "alg_flops": st["alg_flops"], "ms_symbolic_host": st["ms_symbolic"], "ms_ingest": st["ms_ingest"],
-                      "ms_phase1": st["ms_phase1"], "ms_phase2": st["ms_phase2"], "k_AB": float(rates[0]),
+                      "ms_phase1": st["ms_phase1"], "ms_phase2": st["ms_phase2"],
+                      "cuda_graph": os.environ.get("NGT_B200_NO_GRAPH") is None, "k_AB": float(rates[0]),
                       "k_BA": float(rates[1]), "k_AB_e2e": kab},
         }
     barrier()

@@ -137,6 +137,10 @@ int ngt_reduced_block_dev(ngt_handle h, double **dptr, int64_t *ndoubles);
 int ngt_phase_two_shard(ngt_handle h, int32_t rank, int32_t nranks);
 int ngt_set_final(ngt_handle h, const double *omPxx, const double *tau);   /* install merged results */
 
+/* Device buffers of destroyed handles are cached per process for reuse by later handles (cudaMalloc/cudaFree of the
+ * front pools cost ~0.1 s).  This returns the cached memory to the driver. */
+void ngt_trim_device_cache(void);
+
 const char *ngt_last_error(void);
 const char *ngt_version(void);
 

@@ -42,7 +42,10 @@ class Stats(ctypes.Structure):
     ]
 
     def as_dict(self):
-        return {f: getattr(self, f) for f, _t in self._fields_ if f != "reserved"}
+        d = {f: getattr(self, f) for f, _t in self._fields_ if f != "reserved"}
+        d["schur_launches"] = self.reserved[0]
+        d["ms_profiled_pass"] = self.reserved[1]
+        return d
 
 
 class NGTNumericError(ArithmeticError):
@@ -100,6 +103,8 @@ def lib():
         f.restype = ctypes.c_int
     L.ngt_destroy.argtypes = [H]
     L.ngt_destroy.restype = None
+    L.ngt_trim_device_cache.argtypes = []
+    L.ngt_trim_device_cache.restype = None
     L.ngt_last_error.restype = ctypes.c_char_p
     L.ngt_version.restype = ctypes.c_char_p
     _lib = L
@@ -111,7 +116,8 @@ EXPORTED_SYMBOLS = [
     "ngt_destroy", "ngt_compute_rates", "ngt_compute_rates_and_committors", "ngt_phase_one", "ngt_phase_two",
     "ngt_get_rates", "ngt_get_final", "ngt_get_reduced", "ngt_get_initial_tau", "ngt_get_committors", "ngt_get_mfpt",
     "ngt_get_stats", "ngt_timed_steps", "ngt_profile_schur", "ngt_batch_create", "ngt_batch_create_dense", "ngt_batch_create_dense_dev", "ngt_batch_get_rates",
-    "ngt_reduced_block_dev", "ngt_phase_two_shard", "ngt_set_final", "ngt_last_error", "ngt_version",
+    "ngt_reduced_block_dev", "ngt_phase_two_shard", "ngt_set_final", "ngt_trim_device_cache", "ngt_last_error",
+    "ngt_version",
 ]
 
 

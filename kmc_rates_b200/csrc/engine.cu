@@ -17,8 +17,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -46,23 +49,95 @@ struct NumericError : std::runtime_error {
                             std::to_string(__LINE__) + ")");                                              \
     } while (0)
 
+// Process-wide cache of device allocations.  cudaMalloc / cudaFree of the multi-hundred-MB front pools cost up to
+// ~100 ms each (cudaFree also synchronises the device); a sweep that creates and destroys handles would pay that per
+// network.  Freed blocks are kept (up to a cap) and handed back to the next handle on the same device.
+struct DevCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void *> blocks;   // (device, bytes) -> pointer
+    size_t cached = 0;
+    static constexpr size_t CAP = (size_t)24 << 30;
+
+    void *get(size_t bytes, size_t &cap) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = blocks.lower_bound(std::make_pair(dev, bytes));
+            if (it != blocks.end() && it->first.first == dev && it->first.second <= bytes + bytes / 2 + (1u << 20)) {
+                void *p = it->second;
+                cap = it->first.second;
+                cached -= cap;
+                blocks.erase(it);
+                return p;
+            }
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            trim();   // give cached memory back and retry once
+            e = cudaMalloc(&p, bytes);
+        }
+        if (e != cudaSuccess)
+            throw CudaError(std::string("cudaMalloc(") + std::to_string(bytes) + " bytes): " + cudaGetErrorString(e));
+        cap = bytes;
+        return p;
+    }
+    void put(void *p, size_t cap) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(mu);
+        if (cached + cap > CAP) {
+            cudaFree(p);
+            return;
+        }
+        blocks.emplace(std::make_pair(dev, cap), p);
+        cached += cap;
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lk(mu);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto &kv : blocks) {
+            cudaSetDevice(kv.first.first);
+            cudaFree(kv.second);
+        }
+        cudaSetDevice(cur);
+        blocks.clear();
+        cached = 0;
+    }
+};
+DevCache g_cache;
+
 template <class T>
 struct DevBuf {
     T *p = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p; n = o.n; cap = o.cap;
+            o.p = nullptr; o.n = o.cap = 0;
+        }
+        return *this;
+    }
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+        if (count) p = static_cast<T *>(g_cache.get(count * sizeof(T), cap));
     }
     void upload(const std::vector<T> &v) {
         alloc(v.size());
         if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) g_cache.put(p, cap);
         p = nullptr;
-        n = 0;
+        n = cap = 0;
     }
     ~DevBuf() { release(); }
 };
@@ -137,6 +212,11 @@ struct Engine {
 
     bool use_big_kernel = std::getenv("NGT_B200_BIG") != nullptr;   // 128 x 128 kernel: measured slower than 2 CTAs/SM of 128 x 64
     bool use_lookahead = std::getenv("NGT_B200_NO_LOOKAHEAD") == nullptr;
+    bool use_graph = std::getenv("NGT_B200_NO_GRAPH") == nullptr;
+    bool capturing = false, last_step_graph = false;
+    long long steps_done = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    const double *graph_dK = nullptr;
     bool d2_pending = false;
     cudaStream_t stream2 = nullptr;
     cudaEvent_t sync_ev[2] = {nullptr, nullptr};
@@ -157,9 +237,12 @@ struct Engine {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     ~Engine() {
+        if (stream) cudaStreamSynchronize(stream);
+        if (stream2) cudaStreamSynchronize(stream2);
         for (auto &e : ev)
             if (e) cudaEventDestroy(e);
         for (auto &e : prof_ev) cudaEventDestroy(e);
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
         for (auto &e : sync_ev)
             if (e) cudaEventDestroy(e);
         if (stream2) cudaStreamDestroy(stream2);
@@ -201,6 +284,7 @@ struct Engine {
         for (auto &x : ev) CK(cudaEventCreate(&x));
         d_err.alloc(1);
         CK(cudaMemset(d_err.p, 0, sizeof(int)));
+        ngt::init_kernel_attributes();
     }
 
     void validate_groups() {
@@ -481,14 +565,15 @@ struct Engine {
 
     void phase_one() {
         if (!values_loaded) throw StateError("no rate constants loaded");
+        if (!capturing) last_step_graph = false;
         CK(cudaSetDevice(device));
         st.n_launches = 0;
         st.schur_flops = 0;
         st.reserved[0] = 0;
         prof_used = 0;
-        CK(cudaEventRecord(ev[0], stream));
+        if (!capturing) CK(cudaEventRecord(ev[0], stream));
         ingest();
-        CK(cudaEventRecord(ev[1], stream));
+        if (!capturing) CK(cudaEventRecord(ev[1], stream));
         ngt::LaunchCtx c = ctx(d_pool.p, pool_stride, d_fronts.p);
         size_t ri = 0, bi = 0;
         for (int l = 0; l < S.n_levels; ++l) {
@@ -499,7 +584,7 @@ struct Engine {
             }
             for (; bi < batches.size() && S.batches[bi].level == l; ++bi) eliminate(c, batches[bi], d_ids.p);
         }
-        CK(cudaEventRecord(ev[2], stream));
+        if (!capturing) CK(cudaEventRecord(ev[2], stream));
         have_phase1 = true;
         have_phase2 = false;
         have_backsub = false;
@@ -530,7 +615,7 @@ struct Engine {
     void phase_two_enqueue(int rank = 0, int nranks = 1) {
         if (!have_phase1) throw StateError("phase_two called before phase_one");
         CK(cudaSetDevice(device));
-        CK(cudaEventRecord(ev[3], stream));
+        if (!capturing) CK(cudaEventRecord(ev[3], stream));
         const DFront R{S.fronts[S.root_id].off, S.fronts[S.root_id].f, 0, S.fronts[S.root_id].ld, -1};
         ngt::LaunchCtx c1 = ctx(d_pool.p, pool_stride, d_fronts.p);
         ngt::LaunchCtx c2 = ctx(d_p2pool.p, p2_stride, d_p2fronts.p);
@@ -564,7 +649,49 @@ struct Engine {
                                        rank, nranks);
             st.n_launches++;
         }
-        CK(cudaEventRecord(ev[4], stream));
+        if (!capturing) CK(cudaEventRecord(ev[4], stream));
+    }
+
+    // One whole numeric step (ingest + phase 1 + phase 2 kernels).  The launch sequence depends only on the
+    // symbolic structure, so it is captured once into a CUDA graph (both streams, their event dependencies and the
+    // memsets included) and replayed: ~400 dependent small launches cost one graph launch.
+    void step_enqueue() {
+        // A single step is cheaper launched directly (capture + instantiation cost a few ms); steps dominated by
+        // a few long tensor-bound launches (one huge front) gain nothing from a graph and keep their stream priorities.
+        if (!use_graph || profile_schur || steps_done < 1 || S.max_front > 4096) {
+            last_step_graph = false;
+            phase_one();
+            phase_two_enqueue();
+            ++steps_done;
+            return;
+        }
+        CK(cudaSetDevice(device));
+        if (!graph_exec || graph_dK != d_K) {
+            if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+            cudaGraph_t g = nullptr;
+            capturing = true;
+            CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
+            try {
+                phase_one();
+                phase_two_enqueue();
+            } catch (...) {
+                cudaStreamEndCapture(stream, &g);
+                if (g) cudaGraphDestroy(g);
+                capturing = false;
+                throw;
+            }
+            capturing = false;
+            CK(cudaStreamEndCapture(stream, &g));
+            cudaError_t ie = cudaGraphInstantiate(&graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { graph_exec = nullptr; throw CudaError(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+            graph_dK = d_K;
+        }
+        CK(cudaGraphLaunch(graph_exec, stream));
+        last_step_graph = true;
+        have_phase1 = true;
+        have_phase2 = false;
+        have_backsub = false;
     }
 
     void phase_two_finish(int nranks = 1) {
@@ -575,10 +702,12 @@ struct Engine {
         download_root();
         check_errflag("phase two");
         shard_ids.clear();
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ev[0], ev[1]); st.ms_ingest = ms;
-        cudaEventElapsedTime(&ms, ev[1], ev[2]); st.ms_phase1 = ms;
-        cudaEventElapsedTime(&ms, ev[3], ev[4]); st.ms_phase2 = ms;
+        if (!last_step_graph) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[0], ev[1]); st.ms_ingest = ms;
+            cudaEventElapsedTime(&ms, ev[1], ev[2]); st.ms_phase1 = ms;
+            cudaEventElapsedTime(&ms, ev[3], ev[4]); st.ms_phase2 = ms;
+        }
         have_phase2 = true;
         if (nranks == 1) finish_rates();
     }
@@ -704,33 +833,70 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
     std::vector<int64_t> fill(outdeg.begin(), outdeg.end() - 1);
     std::vector<int32_t> ent(nnz);
     for (int64_t e = 0; e < nnz; ++e) ent[fill[src[e]]++] = (int32_t)e;   // stable: increasing e inside a row
-    std::vector<long long> row_ptr;
-    std::vector<int> row_node, korig;
-    std::vector<long long> dest, tau_dest;
-    row_ptr.push_back(0);
-    std::vector<int32_t> rowbuf;
-    for (int64_t u = 0; u < n; ++u) {
-        if (!present[u]) continue;
-        rowbuf.assign(ent.begin() + outdeg[u], ent.begin() + outdeg[u + 1]);
-        std::stable_sort(rowbuf.begin(), rowbuf.end(), [&](int32_t a, int32_t b) { return dst[a] < dst[b]; });
-        const int32_t pu = S.pos[u];
-        for (size_t i = 0; i < rowbuf.size(); ++i) {
-            if (i + 1 < rowbuf.size() && dst[rowbuf[i + 1]] == dst[rowbuf[i]]) continue;   // keep the last duplicate
-            const int32_t e = rowbuf[i];
-            const int32_t pv = S.pos[dst[e]];
-            const int32_t owner = S.pos_front[std::min(pu, pv)];
-            const ngt::Front &F = S.fronts[owner];
-            const int32_t lr = ngt::local_index(S, owner, pu), lc = ngt::local_index(S, owner, pv);
-            if (lr < 0 || lc < 0) throw std::logic_error("ingest: entry has no slot in its front");
-            korig.push_back(e);
-            dest.push_back(F.off + (long long)lr * F.ld + lc);
-        }
-        row_ptr.push_back((long long)korig.size());
-        row_node.push_back((int)u);
-        const int32_t owner = S.pos_front[pu];
-        const ngt::Front &F = S.fronts[owner];
-        const int32_t lr = ngt::local_index(S, owner, pu);
-        tau_dest.push_back(F.off + (long long)lr * F.ld + F.f);
+    // rows = present nodes in id order; each worker thread handles a contiguous slice of rows twice:
+    // pass 1 counts the entries that survive de-duplication, pass 2 writes source indices and slots.
+    std::vector<int> row_node;
+    for (int64_t u = 0; u < n; ++u)
+        if (present[u]) row_node.push_back((int)u);
+    const int64_t nrows = (int64_t)row_node.size();
+    std::vector<long long> row_ptr(nrows + 1, 0), tau_dest(nrows);
+    std::vector<int> korig;
+    std::vector<long long> dest;
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        int nthr = (int)std::max(1u, std::min(hw ? hw : 1u, 32u));
+        if (nrows < 4096) nthr = 1;
+        std::vector<std::vector<int32_t> > marks(nthr);
+        auto dedup_row = [&](int64_t u, std::vector<int32_t> &mark, auto &&emit) {
+            // later duplicates win: walk the row backwards and keep the first sighting of every destination
+            for (int64_t q = outdeg[u + 1]; q-- > outdeg[u];) {
+                const int32_t e = ent[q];
+                const int64_t v = dst[e];
+                if (mark[v] == (int32_t)u) continue;
+                mark[v] = (int32_t)u;
+                emit(e);
+            }
+        };
+        auto run = [&](auto &&body) {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nthr; ++t) th.emplace_back([&, t] { body(t, nrows * t / nthr, nrows * (t + 1) / nthr); });
+            for (auto &x : th) x.join();
+        };
+        run([&](int t, int64_t r0, int64_t r1) {
+            marks[t].assign(n, -1);
+            for (int64_t r = r0; r < r1; ++r) {
+                long long c = 0;
+                dedup_row(row_node[r], marks[t], [&](int32_t) { ++c; });
+                row_ptr[r + 1] = c;
+            }
+        });
+        for (int64_t r = 0; r < nrows; ++r) row_ptr[r + 1] += row_ptr[r];
+        korig.resize(row_ptr[nrows]);
+        dest.resize(row_ptr[nrows]);
+        std::vector<char> bad(nthr, 0);
+        run([&](int t, int64_t r0, int64_t r1) {
+            std::fill(marks[t].begin(), marks[t].end(), -1);
+            for (int64_t r = r0; r < r1; ++r) {
+                const int64_t u = row_node[r];
+                const int32_t pu = S.pos[u];
+                long long w = row_ptr[r];
+                dedup_row(u, marks[t], [&](int32_t e) {
+                    const int32_t pv = S.pos[dst[e]];
+                    const int32_t owner = S.pos_front[std::min(pu, pv)];
+                    const ngt::Front &F = S.fronts[owner];
+                    const int32_t lr = ngt::local_index(S, owner, pu), lc = ngt::local_index(S, owner, pv);
+                    if (lr < 0 || lc < 0) bad[t] = 1;
+                    korig[w] = e;
+                    dest[w] = F.off + (long long)lr * F.ld + lc;
+                    ++w;
+                });
+                const int32_t owner = S.pos_front[pu];
+                const ngt::Front &F = S.fronts[owner];
+                tau_dest[r] = F.off + (long long)ngt::local_index(S, owner, pu) * F.ld + F.f;
+            }
+        });
+        for (char b : bad)
+            if (b) throw std::logic_error("ingest: entry has no slot in its front");
     }
     E->n_rows = (int)row_node.size();
     tm.lap("CSR + slot table");
@@ -945,16 +1111,16 @@ int ngt_phase_two_shard(ngt_handle h, int32_t rank, int32_t nranks) {
 int ngt_compute_rates(ngt_handle h) {
     return guard([&] {
         Engine *E = eng(h);
-        E->phase_one();
-        E->phase_two();
+        E->step_enqueue();
+        E->phase_two_finish();
     });
 }
 
 int ngt_compute_rates_and_committors(ngt_handle h) {
     return guard([&] {
         Engine *E = eng(h);
-        E->phase_one();
-        E->phase_two();
+        E->step_enqueue();
+        E->phase_two_finish();
         E->backsub();
     });
 }
@@ -1049,10 +1215,7 @@ int ngt_timed_steps(ngt_handle h, int32_t steps, double *ms_total) {
         CK(cudaSetDevice(E->device));
         CK(cudaStreamSynchronize(E->stream));
         CK(cudaEventRecord(E->ev[5], E->stream));
-        for (int i = 0; i < steps; ++i) {
-            E->phase_one();
-            E->phase_two_enqueue();
-        }
+        for (int i = 0; i < steps; ++i) E->step_enqueue();
         cudaEvent_t stop = E->prof_event();
         CK(cudaEventRecord(stop, E->stream));
         CK(cudaStreamSynchronize(E->stream));
@@ -1064,6 +1227,8 @@ int ngt_timed_steps(ngt_handle h, int32_t steps, double *ms_total) {
 }
 
 int ngt_profile_schur(ngt_handle h, double *ms_schur, double *flops, int64_t *launches) {
+    // reserved[1] of ngt_stats receives the duration of the whole profiled phase-1 pass (same pass, same event
+    // overheads), so that the kernel's share of the step can be formed from consistent numbers
     return guard([&] {
         Engine *E = eng(h);
         CK(cudaSetDevice(E->device));
@@ -1084,11 +1249,16 @@ int ngt_profile_schur(ngt_handle h, double *ms_schur, double *flops, int64_t *la
             tot += ms;
         }
         E->st.ms_schur = tot;
+        float pass_ms = 0;
+        CK(cudaEventElapsedTime(&pass_ms, E->ev[0], E->ev[2]));
+        E->st.reserved[1] = pass_ms;
         *ms_schur = tot;
         *flops = E->st.schur_flops;
         *launches = (int64_t)(E->prof_used / 2);
     });
 }
+
+void ngt_trim_device_cache(void) { g_cache.trim(); }
 
 int ngt_reduced_block_dev(ngt_handle h, double **dptr, int64_t *ndoubles) {
     return guard([&] {

@@ -530,26 +530,23 @@ update_dmma_big_kernel(double *pool, long long pool_stride, const DFront *fronts
 int update_tile_m(int gemm_path) { return gemm_path == 1 ? FT : (gemm_path == 2 ? BM : TM); }
 int update_tile_n(int gemm_path) { return gemm_path == 1 ? FT : (gemm_path == 2 ? BN : TN); }
 
+void init_kernel_attributes() {
+    cudaFuncSetAttribute(update_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)((size_t)TSTG * TSTAGE_DOUBLES * sizeof(double)));
+    cudaFuncSetAttribute(update_dmma_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)((size_t)STG * STAGE_DOUBLES * sizeof(double)));
+}
+
 void launch_update(const LaunchCtx &c, const int *ids, int nfb, int j, int mode, int max_tiles, int split) {
     if (max_tiles <= 0) return;
     dim3 grid(max_tiles, nfb, c.nbatch);
     if (c.gemm_path == 1) {
         update_dfma_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split);
     } else if (c.gemm_path == 2) {
-        static bool big_attr_set = false;
         const size_t smem = (size_t)STG * STAGE_DOUBLES * sizeof(double);
-        if (!big_attr_set) {
-            cudaFuncSetAttribute(update_dmma_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            big_attr_set = true;
-        }
         update_dmma_big_kernel<<<grid, 512, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split);
     } else {
-        static bool attr_set = false;
         const size_t smem = (size_t)TSTG * TSTAGE_DOUBLES * sizeof(double);
-        if (!attr_set) {
-            cudaFuncSetAttribute(update_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
-        }
         update_dmma_kernel<<<grid, 256, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split);
     }
 }

@@ -94,6 +94,9 @@ void launch_rowpanel(const LaunchCtx &c, const int *ids, int nfb, int j, int max
 // mode MODE_AB runs both L-shaped regions in one launch: CTAs [0, split) do MODE_A, the rest MODE_B
 void launch_update(const LaunchCtx &c, const int *ids, int nfb, int j, int mode, int max_tiles, int split);
 
+// opt-in shared-memory sizes of the DMMA kernels (call once per process/device before the first launch)
+void init_kernel_attributes();
+
 // tile geometry used by the host to size grids
 int update_tile_m(int gemm_path);
 int update_tile_n(int gemm_path);

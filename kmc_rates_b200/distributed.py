@@ -1,0 +1,84 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed; NCCL on GPUs, gloo in the CPU tests).
+
+Only the parts of the path that shard are here:
+
+* independent networks (BASELINE config 5, temperature sweeps): `shard_range` gives every rank a contiguous block of
+  networks; no data-path collective, results are gathered at the end (`gather_rates`);
+* phase 2 (BASELINE config 4): the per-a reductions are independent once the reduced A ∪ B block exists.  Every rank
+  runs `ngt_phase_two_shard(rank, world)` on every world-th a and the (1-P'_aa, tau'_a) pairs are merged with ONE
+  all-reduce(sum) (unowned entries are zero) and installed with `ngt_set_final`.  Optionally rank 0's reduced block is
+  broadcast first so that every rank reduces bit-identical input.
+
+The reference has nothing to compare with here: it is single-threaded ("Parallelism strategies: none").
+"""
+import numpy as np
+
+
+def shard_range(n_items, rank, world):
+    """contiguous block [lo, hi) of `n_items` for `rank` (sizes differ by at most one)"""
+    base, extra = divmod(int(n_items), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def all_reduce_sum(array, group=None):
+    """sum a float64 numpy array over the ranks of `group` (moves through the GPU when the backend is NCCL)"""
+    import torch
+    dist = _dist()
+    t = torch.from_numpy(np.ascontiguousarray(array, np.float64).copy())
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+class _DeviceBlock(object):
+    """exposes a raw device pointer through __cuda_array_interface__ so torch can broadcast it in place"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+
+def broadcast_reduced_block(handle, src=0, group=None):
+    """NCCL broadcast of the phase-1-reduced (|A|+|B|) x ld block (incl. tau column) from rank `src` into every rank's
+    engine memory (8 MiB at |A|+|B| = 1024)."""
+    import torch
+    ptr, n = handle.reduced_block_dev()
+    t = torch.as_tensor(_DeviceBlock(ptr, n), device="cuda")
+    _dist().broadcast(t, src=src, group=group)
+    torch.cuda.synchronize()
+
+
+def phase_two_sharded(handle, rank, world, reduce_fn=all_reduce_sum):
+    """per-a reductions of this rank's share + one all-reduce; afterwards every rank's handle returns the full rates.
+    `handle` needs phase_two_shard(rank, world), final() -> (om, tau) and set_final(om, tau)."""
+    handle.phase_two_shard(rank, world)
+    om, tau = handle.final()
+    m = om.size
+    merged = reduce_fn(np.concatenate([om, tau]))
+    handle.set_final(merged[:m], merged[m:])
+    return merged[:m], merged[m:]
+
+
+def compute_rates_sharded(handle, group=None, broadcast=False):
+    """phase 1 on every rank (replicated), optional broadcast of rank 0's reduced block, sharded phase 2."""
+    dist = _dist()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    handle.phase_one()
+    if broadcast and world > 1:
+        broadcast_reduced_block(handle, 0, group)
+    return phase_two_sharded(handle, rank, world, lambda a: all_reduce_sum(a, group))
+
+
+def gather_rates(local_rates, n_total, rank, world, group=None):
+    """all-gather per-network rate rows computed on contiguous shards (uses an all-reduce of a zero-padded array)"""
+    local_rates = np.asarray(local_rates, np.float64)
+    lo, hi = shard_range(n_total, rank, world)
+    full = np.zeros((n_total,) + local_rates.shape[1:])
+    full[lo:hi] = local_rates
+    return all_reduce_sum(full, group)
