@@ -162,10 +162,152 @@ panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const in
     }
 }
 
+// =====================================================================================================
+// throughput variant of the panel kernel for launches with many fronts (leaf levels, batched networks, phase-2
+// tasks): 256 threads, each thread owns 4 columns of one row, so 4+ panels are resident per SM and their
+// latency-bound Gauss-Jordan chains overlap.  Same arithmetic, same order of operations per element.
+// =====================================================================================================
+__global__ void __launch_bounds__(256, 4)
+panel_tp_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j,
+                double *wbuf, const double *rsbuf, int maxfb, int maxchunks, int *errflag) {
+    const DFront F = fronts[ids[blockIdx.x]];
+    if (j >= F.k) return;
+    double *M = pool + (long long)blockIdx.y * pool_stride + F.off;
+    const int nbp = min(NB_INNER, F.k - j);
+    const int je = j + nbp;
+    const int u = threadIdx.x >> 3, cg = threadIdx.x & 7, q0 = cg * 4;
+    const int lane = threadIdx.x & 31;
+
+    __shared__ double rowT[2][NB_INNER];
+    __shared__ double rowG[2][NB_INNER];
+    __shared__ double rowS[2], rowRD[2];
+    __shared__ double Ds[NB_INNER];
+    __shared__ double Ws[NB_INNER][NB_INNER];
+    __shared__ double xs[NB_INNER][64];
+
+    auto group_sum = [](double v) {   // sum over the 8 lanes that share a row
+        v += __shfl_xor_sync(0xffffffffu, v, 4, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 2, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 1, 8);
+        return v;
+    };
+
+    // NOTE: four rows share a warp here, so every shuffle below is executed by all 32 lanes unconditionally
+    // (rows beyond nbp contribute zeros); only the use of the result is predicated.
+    double s = 0.0;
+    {
+        const bool live_row = u < nbp;
+        if (F.f - je > RS_SPLIT) {
+            const int nch = (F.f - je + RS_CHUNK - 1) / RS_CHUNK;
+            const double *rs = rsbuf + (((long long)blockIdx.y * maxfb + blockIdx.x) * maxchunks) * NB_INNER;
+            if (live_row)
+                for (int ch = cg; ch < nch; ch += 8) s += rs[ch * NB_INNER + u];
+        } else if (live_row) {
+            const double *row = M + (long long)(j + u) * F.ld;
+            double s0 = 0.0, s1 = 0.0;
+            int c = je + cg;
+            for (; c + 8 < F.f; c += 16) { s0 += row[c]; s1 += row[c + 8]; }
+            for (; c < F.f; c += 8) s0 += row[c];
+            s = s0 + s1;
+        }
+        s = group_sum(s);
+        if (!live_row) s = 1.0;   // padding rows behave like isolated absorbing nodes
+    }
+    double t[4], g[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int q = q0 + e;
+        t[e] = (u < nbp && q < nbp && u != q) ? M[(long long)(j + u) * F.ld + j + q] : 0.0;
+        g[e] = (u == q) ? 1.0 : 0.0;
+    }
+    {
+        const double d = group_sum((t[0] + t[1]) + (t[2] + t[3])) + s;
+        if (u == 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { rowT[0][q0 + e] = t[e]; rowG[0][q0 + e] = g[e]; }
+            if (cg == 0) {
+                rowS[0] = s;
+                rowRD[0] = 1.0 / d;
+                Ds[0] = d;
+                if (!(d > 0.0) || isinf(d)) atomicOr(errflag, 1);
+            }
+        }
+    }
+    for (int p = 0; p < nbp; ++p) {
+        __syncthreads();
+        const int b = p & 1;
+        // T[u][p] lives in element p&3 of the lane with column group p>>2
+        const int pe = p & 3;
+        const double mine = pe == 0 ? t[0] : pe == 1 ? t[1] : pe == 2 ? t[2] : t[3];
+        const double tup = __shfl_sync(0xffffffffu, mine, (lane & ~7) | (p >> 2));
+        if (u != p) {
+            const double sp = rowS[b], rd = rowRD[b];
+            const double fup = (tup == 0.0) ? 0.0 : tup * rd;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int q = q0 + e;
+                t[e] = (q == p || q == u) ? 0.0 : fma(fup, rowT[b][q], t[e]);
+                g[e] = fma(fup, rowG[b][q], g[e]);
+            }
+            s = fma(fup, sp, s);
+        }
+        const double d = group_sum((t[0] + t[1]) + (t[2] + t[3])) + s;   // all lanes, see NOTE
+        if (u == p + 1 && u < nbp) {          // publish the next pivot row one step ahead
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { rowT[b ^ 1][q0 + e] = t[e]; rowG[b ^ 1][q0 + e] = g[e]; }
+            if (cg == 0) {
+                rowS[b ^ 1] = s;
+                rowRD[b ^ 1] = 1.0 / d;
+                Ds[u] = d;
+                if (!(d > 0.0) || isinf(d)) atomicOr(errflag, 1);
+            }
+        }
+    }
+    __syncthreads();
+    double *Wout = wbuf + ((long long)blockIdx.y * maxfb + blockIdx.x) * (NB_INNER * NB_INNER);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const double w = (u < nbp) ? g[e] / Ds[u] : 0.0;
+        Ws[u][q0 + e] = w;
+        Wout[u * NB_INNER + q0 + e] = w;
+    }
+    const int ncols = F.f + 1 - je;
+    if (ncols > FUSE_COLS) return;
+    const int cc = threadIdx.x & 63, r0 = threadIdx.x >> 6;
+    for (int cs = 0; cs < ncols; cs += 64) {
+        __syncthreads();
+        const bool live = cs + cc < ncols;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 4 * i;
+            xs[r][cc] = (live && r < nbp) ? M[(long long)(j + r) * F.ld + je + cs + cc] : 0.0;
+        }
+        __syncthreads();
+        double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+        for (int tt = 0; tt < NB_INNER; ++tt) {
+            const double x = xs[tt][cc];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fma(Ws[r0 + 4 * i][tt], x, acc[i]);
+        }
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 4 * i;
+                if (r < nbp) M[(long long)(j + r) * F.ld + je + cs + cc] = acc[i];
+            }
+        }
+    }
+}
+
 void launch_panel(const LaunchCtx &c, const int *ids, int nfb, int j) {
     dim3 grid(nfb, c.nbatch);
-    panel_kernel<<<grid, 1024, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.rsbuf, c.maxfb,
-                                             c.maxchunks, c.errflag);
+    if ((long long)nfb * c.nbatch >= 2 * 148)   // many panels: favour occupancy over single-panel latency
+        panel_tp_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.rsbuf, c.maxfb,
+                                                   c.maxchunks, c.errflag);
+    else
+        panel_kernel<<<grid, 1024, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.rsbuf, c.maxfb,
+                                                 c.maxchunks, c.errflag);
 }
 
 // =====================================================================================================
