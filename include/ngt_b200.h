@@ -137,6 +137,24 @@ int ngt_reduced_block_dev(ngt_handle h, double **dptr, int64_t *ndoubles);
 int ngt_phase_two_shard(ngt_handle h, int32_t rank, int32_t nranks);
 int ngt_set_final(ngt_handle h, const double *omPxx, const double *tau);   /* install merged results */
 
+/* ---- multi-GPU: ONE dense network over several GPUs (SURVEY §8e, config 3 at N > 1) ----------------------
+ * 1-D block-cyclic column partition (block = *block of ngt_dist_info) with a panel broadcast per outer block.
+ * Every rank creates the same dense handle (ngt_create_dense*), then drives, for J = 0, block, 2*block, ... < n_pivots:
+ *     ngt_dist_rowsum(h, J, &p, &n)     all-reduce(sum) the n doubles at device pointer p over the ranks
+ *     ngt_dist_factor(h, J)             only on the owner, rank (J / block) % world
+ *     ngt_dist_panel(h, J, &p, &n)      broadcast the n doubles at p from the owner
+ *     ngt_dist_apply(h, J)              every rank
+ * and finally ngt_dist_root (all-reduce(sum) its buffer), ngt_dist_finish, then ngt_phase_two / getters as usual.
+ * The collectives are the caller's (NCCL through torch.distributed in kmc_rates_b200/distributed.py). */
+int ngt_dist_begin(ngt_handle h, int32_t rank, int32_t world);
+int ngt_dist_info(ngt_handle h, int64_t *n_pivots, int64_t *block);
+int ngt_dist_rowsum(ngt_handle h, int64_t J, double **dptr, int64_t *ndoubles);
+int ngt_dist_factor(ngt_handle h, int64_t J);
+int ngt_dist_panel(ngt_handle h, int64_t J, double **dptr, int64_t *ndoubles);
+int ngt_dist_apply(ngt_handle h, int64_t J);
+int ngt_dist_root(ngt_handle h, double **dptr, int64_t *ndoubles);
+int ngt_dist_finish(ngt_handle h);
+
 /* Device buffers of destroyed handles are cached per process for reuse by later handles (cudaMalloc/cudaFree of the
  * front pools cost ~0.1 s).  This returns the cached memory to the driver. */
 void ngt_trim_device_cache(void);

@@ -96,6 +96,14 @@ def lib():
         "ngt_reduced_block_dev": [H, ctypes.POINTER(vp), _i64p],
         "ngt_phase_two_shard": [H, ctypes.c_int32, ctypes.c_int32],
         "ngt_set_final": [H, _f64p, _f64p],
+        "ngt_dist_begin": [H, ctypes.c_int32, ctypes.c_int32],
+        "ngt_dist_info": [H, _i64p, _i64p],
+        "ngt_dist_rowsum": [H, i64, ctypes.POINTER(vp), _i64p],
+        "ngt_dist_factor": [H, i64],
+        "ngt_dist_panel": [H, i64, ctypes.POINTER(vp), _i64p],
+        "ngt_dist_apply": [H, i64],
+        "ngt_dist_root": [H, ctypes.POINTER(vp), _i64p],
+        "ngt_dist_finish": [H],
     }
     for name, args in sig.items():
         f = getattr(L, name)
@@ -116,7 +124,9 @@ EXPORTED_SYMBOLS = [
     "ngt_destroy", "ngt_compute_rates", "ngt_compute_rates_and_committors", "ngt_phase_one", "ngt_phase_two",
     "ngt_get_rates", "ngt_get_final", "ngt_get_reduced", "ngt_get_initial_tau", "ngt_get_committors", "ngt_get_mfpt",
     "ngt_get_stats", "ngt_timed_steps", "ngt_profile_schur", "ngt_batch_create", "ngt_batch_create_dense", "ngt_batch_create_dense_dev", "ngt_batch_get_rates",
-    "ngt_reduced_block_dev", "ngt_phase_two_shard", "ngt_set_final", "ngt_trim_device_cache", "ngt_last_error",
+    "ngt_reduced_block_dev", "ngt_phase_two_shard", "ngt_set_final", "ngt_dist_begin", "ngt_dist_info", "ngt_dist_rowsum",
+    "ngt_dist_factor", "ngt_dist_panel", "ngt_dist_apply", "ngt_dist_root", "ngt_dist_finish", "ngt_trim_device_cache",
+    "ngt_last_error",
     "ngt_version",
 ]
 
@@ -322,6 +332,38 @@ class Handle(object):
         ms, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
         check(lib().ngt_profile_schur(self.h, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n)))
         return ms.value, fl.value, n.value
+
+    # ---- one dense network over several GPUs (see include/ngt_b200.h) ------------------------------------
+    def _ptr_call(self, fn, *args):
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        check(fn(self.h, *args, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def dist_begin(self, rank, world):
+        check(lib().ngt_dist_begin(self.h, int(rank), int(world)))
+
+    def dist_info(self):
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        check(lib().ngt_dist_info(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def dist_rowsum(self, J):
+        return self._ptr_call(lib().ngt_dist_rowsum, int(J))
+
+    def dist_factor(self, J):
+        check(lib().ngt_dist_factor(self.h, int(J)))
+
+    def dist_panel(self, J):
+        return self._ptr_call(lib().ngt_dist_panel, int(J))
+
+    def dist_apply(self, J):
+        check(lib().ngt_dist_apply(self.h, int(J)))
+
+    def dist_root(self):
+        return self._ptr_call(lib().ngt_dist_root)
+
+    def dist_finish(self):
+        check(lib().ngt_dist_finish(self.h))
 
     def reduced_block_dev(self):
         p = ctypes.c_void_p()

@@ -149,6 +149,7 @@ using ngt::Symbolic;
 struct HostBatch {
     std::vector<int> ids;     // front ids
     std::vector<int> f, k;    // their order and pivot count (for grid sizing)
+    std::vector<int> fr;      // row counts of rectangular fronts (empty = square)
     size_t dev_off = 0;       // offset into the device id array
     int max_k = 0;
 };
@@ -218,6 +219,7 @@ struct Engine {
     cudaGraphExec_t graph_exec = nullptr;
     const double *graph_dK = nullptr;
     bool d2_pending = false;
+    bool wslot_per_step = false;
     cudaStream_t stream2 = nullptr;
     cudaEvent_t sync_ev[2] = {nullptr, nullptr};
     cudaEvent_t sync_event(int i) { return sync_ev[i]; }
@@ -262,6 +264,7 @@ struct Engine {
         c.errflag = d_err.p;
         c.stream = stream;
         c.gemm_path = opt.gemm_path;
+        c.ko = ngt::KOpt{0, 0, 0, ngt::FUSE_COLS};
         return c;
     }
 
@@ -408,7 +411,7 @@ struct Engine {
             const int ng = ngs[g];
             HostBatch hb;
             for (int t = 0; t < ng; ++t) {
-                DFront F;
+                DFront F{};
                 F.f = ng + 1;
                 F.k = ng - 1;
                 F.ld = ((F.f + 1 + 7) / 8) * 8;
@@ -444,7 +447,7 @@ struct Engine {
         int mx = 0;
         ngt::Region R;
         for (size_t i = 0; i < b.ids.size(); ++i) {
-            if (!ngt::get_region(b.f[i], b.k[i], j, mode, R)) continue;
+            if (!ngt::get_region(b.f[i], b.fr.empty() ? 0 : b.fr[i], b.k[i], j, mode, R)) continue;
             const int t = ((R.r1 - R.r0 + tm - 1) / tm) * ((R.c1 - R.c0 + tn - 1) / tn);
             mx = std::max(mx, t);
             flops += 2.0 * (R.r1 - R.r0) * (double)(R.c1 - R.c0) * (R.k1 - R.k0);
@@ -479,17 +482,19 @@ struct Engine {
         const int tm = ngt::update_tile_m(opt.gemm_path), tn = ngt::update_tile_n(opt.gemm_path);
         const int *ids = dev_ids + b.dev_off;
         for (int j = 0; j < b.max_k; j += ngt::NB_INNER) {
+            ngt::LaunchCtx cj = c;
+            if (wslot_per_step) cj.ko.wslot = (j % ngt::NB_OUTER) / ngt::NB_INNER;   // keep every W of the outer block
             int max_cols = 0;   // columns right of the panel incl. the tau column, widest live front
             for (int i = 0; i < nfb; ++i)
                 if (b.k[i] > j) max_cols = std::max(max_cols, b.f[i] + 1 - std::min(j + ngt::NB_INNER, b.k[i]));
             if (max_cols - 1 > ngt::RS_SPLIT) {
-                ngt::launch_rowsum(c, ids, nfb, j, max_cols - 1);
+                ngt::launch_rowsum(cj, ids, nfb, j, max_cols - 1);
                 st.n_launches++;
             }
-            ngt::launch_panel(c, ids, nfb, j);
+            ngt::launch_panel(cj, ids, nfb, j);
             st.n_launches++;
-            if (max_cols > ngt::FUSE_COLS) {
-                ngt::launch_rowpanel(c, ids, nfb, j, max_cols);
+            if (max_cols > cj.ko.fuse_cols) {
+                ngt::launch_rowpanel(cj, ids, nfb, j, max_cols);
                 st.n_launches++;
             }
             double fl = 0, dummy = 0;
@@ -501,7 +506,7 @@ struct Engine {
             st.schur_flops += fl * nbatch;
             // large trailing regions run on the 128 x 128 kernel when they fill the machine (>= 2 waves of big
             // tiles); small regions keep the 128 x 64 kernel (more CTAs)
-            ngt::LaunchCtx c2 = c;
+            ngt::LaunchCtx c2 = cj;
             bool d2_async = false;
             if (td2 > 0) {
                 long long live = 0;
@@ -522,7 +527,7 @@ struct Engine {
                 st.n_launches++;
                 st.reserved[0] += 1;   // Schur-update launches
             };
-            if (ta + tb > 0) timed(stream, [&] { ngt::launch_update(c, ids, nfb, j, ngt::MODE_AB, ta + tb, ta); });
+            if (ta + tb > 0) timed(stream, [&] { ngt::launch_update(cj, ids, nfb, j, ngt::MODE_AB, ta + tb, ta); });
             if (td1a + td1b + td2 > 0) {
                 if (d2_async) {
                     // D2 needs the finished panels of this outer block ...
@@ -532,7 +537,7 @@ struct Engine {
                 if (td1a + td1b > 0) {
                     // ... D1 touches the region the previous D2 was writing
                     if (d2_pending) { CK(cudaStreamWaitEvent(stream, sync_event(1), 0)); d2_pending = false; }
-                    timed(stream, [&] { ngt::launch_update(c, ids, nfb, j, ngt::MODE_D1, td1a + td1b, td1a); });
+                    timed(stream, [&] { ngt::launch_update(cj, ids, nfb, j, ngt::MODE_D1, td1a + td1b, td1a); });
                 }
                 if (td2 > 0) {
                     if (d2_async) {
@@ -567,9 +572,9 @@ struct Engine {
         CK(cudaMemsetAsync(d_pool.p, 0, (size_t)pool_stride * nbatch * sizeof(double), stream));
         if (dense) {
             const int f0 = S.nI > 0 ? 0 : S.root_id;
-            DFront F0, R;
+            DFront F0{}, R{};
             auto cv = [&](int id) {
-                DFront d;
+                DFront d{};
                 d.off = S.fronts[id].off; d.f = S.fronts[id].f; d.k = S.fronts[id].k; d.ld = S.fronts[id].ld;
                 d.parent = S.fronts[id].parent;
                 return d;
@@ -759,6 +764,159 @@ struct Engine {
                 rates[(size_t)b * 4 + 2 + g] = ss / norm;
             }
         }
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // Single dense network over several GPUs: 1-D block-cyclic columns (block = NB_OUTER), panel broadcast.
+    // The collectives themselves are issued by the host language over torch.distributed / NCCL on the device
+    // pointers these methods hand out (kmc_rates_b200/distributed.py); each method is synchronous on return.
+    // ---------------------------------------------------------------------------------------------
+    int dist_G = 0, dist_g = 0;
+    static constexpr int LD_PAN = ngt::NB_OUTER + 8;
+    static constexpr int W_DOUBLES = (ngt::NB_OUTER / ngt::NB_INNER) * ngt::NB_INNER * ngt::NB_INNER;
+    DevBuf<double> d_pan, d_spart, d_tauglob, d_rootc;
+    DevBuf<DFront> d_dfronts;   // [0] panel front, [1] big matrix with the panel as A operand
+    DevBuf<int> d_dids;
+
+    ngt::KOpt own() const { return ngt::KOpt{dist_G, dist_g, 0, 0}; }
+
+    void dist_begin(int g, int G) {
+        if (!dense || nbatch != 1) throw InvalidError("the multi-GPU dense path needs one complete network (ngt_create_dense*)");
+        if (G < 1 || g < 0 || g >= G) throw InvalidError("bad rank / world size");
+        if (S.nI <= 0) throw InvalidError("no intermediate nodes to eliminate");
+        if (!values_loaded) throw StateError("no rate constants loaded");
+        CK(cudaSetDevice(device));
+        dist_G = G;
+        dist_g = g;
+        const ngt::Front &F0 = S.fronts[0];
+        d_pan.alloc((size_t)W_DOUBLES + (size_t)F0.f * LD_PAN);
+        d_spart.alloc(ngt::NB_OUTER);
+        d_tauglob.alloc((size_t)n);
+        d_rootc.alloc((size_t)m * m);
+        d_dfronts.alloc(2);
+        d_dids.upload(std::vector<int>{0, 1});
+        maxfb = std::max(maxfb, ngt::NB_OUTER / ngt::NB_INNER);
+        d_wbuf.alloc((size_t)nbatch * maxfb * ngt::NB_INNER * ngt::NB_INNER);
+        st.n_launches = 0;
+        st.schur_flops = 0;
+        ingest();
+        ngt::launch_dist_tau_init(d_tau0.p, d_pos.p, (int)n, d_tauglob.p, stream);
+        CK(cudaStreamSynchronize(stream));
+        check_errflag("ingest");
+        have_phase1 = have_phase2 = have_backsub = false;
+    }
+
+    void dist_check(int J) const {
+        if (dist_G < 1) throw StateError("ngt_dist_begin has not been called");
+        if (J < 0 || J >= S.nI || J % ngt::NB_OUTER) throw InvalidError("J must be a multiple of the outer block inside the pivot range");
+    }
+    int block_end(int J) const { return (int)std::min<int64_t>(J + ngt::NB_OUTER, S.nI); }
+
+    // partial mass of the block rows into this rank's columns right of the block -> d_spart (to be all-reduced)
+    double *dist_rowsum(int J) {
+        dist_check(J);
+        const ngt::Front &F0 = S.fronts[0];
+        const int JE = block_end(J);
+        CK(cudaMemsetAsync(d_spart.p, 0, ngt::NB_OUTER * sizeof(double), stream));
+        ngt::launch_dist_rowsum(d_pool.p + F0.off, F0.ld, F0.f, J, JE, own(), d_spart.p, stream);
+        CK(cudaStreamSynchronize(stream));
+        return d_spart.p;
+    }
+
+    // owner: build the panel front from its own columns and factor it with the ordinary front kernels
+    void dist_factor(int J) {
+        dist_check(J);
+        const ngt::Front &F0 = S.fronts[0];
+        const int JE = block_end(J), kb = JE - J, fr = F0.f - J;
+        double *pan = d_pan.p + W_DOUBLES;
+        ngt::launch_dist_pack(d_pool.p + F0.off, F0.ld, J, kb, fr, pan, LD_PAN, d_spart.p, d_tauglob.p, stream);
+        DFront P{};
+        P.off = pan - d_pool.p;          // the kernels address fronts relative to the pool base
+        P.f = kb + 1;                    // kb block columns + S; column kb+1 is tau
+        P.k = kb;
+        P.ld = LD_PAN;
+        P.parent = -1;
+        P.fr = fr;
+        CK(cudaMemcpyAsync(d_dfronts.p, &P, sizeof(DFront), cudaMemcpyHostToDevice, stream));
+        HostBatch hb;
+        hb.ids = {0}; hb.f = {P.f}; hb.k = {P.k}; hb.fr = {fr}; hb.max_k = kb; hb.dev_off = 0;
+        ngt::LaunchCtx c = ctx(d_pool.p, pool_stride, d_dfronts.p);
+        wslot_per_step = true;
+        const bool la = use_lookahead;
+        use_lookahead = false;
+        try {
+            eliminate_chunk(c, hb, d_dids.p);
+        } catch (...) {
+            wslot_per_step = false;
+            use_lookahead = la;
+            throw;
+        }
+        wslot_per_step = false;
+        use_lookahead = la;
+        CK(cudaMemcpyAsync(d_pan.p, d_wbuf.p, W_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+
+    // what travels: [W of the block's inner panels | panel front rows J..f-1]
+    void dist_panel(int J, double **ptr, int64_t *cnt) {
+        dist_check(J);
+        *ptr = d_pan.p;
+        *cnt = (int64_t)W_DOUBLES + (int64_t)(S.fronts[0].f - J) * LD_PAN;
+    }
+
+    // everybody: replay the block's row operations on the own columns, then the trailing update with the panel as A
+    void dist_apply(int J) {
+        dist_check(J);
+        const ngt::Front &F0 = S.fronts[0];
+        const int JE = block_end(J), kb = JE - J, fr = F0.f - J;
+        const double *pan = d_pan.p + W_DOUBLES;
+        CK(cudaMemcpyAsync(d_wbuf.p, d_pan.p, W_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        ngt::launch_dist_tau(pan, LD_PAN, kb, fr, J, d_tauglob.p, stream);
+        DFront B{};
+        B.off = F0.off; B.f = F0.f; B.k = F0.k; B.ld = F0.ld; B.parent = -1; B.fr = 0;
+        B.a_ld = LD_PAN;
+        B.a_off = (pan - d_pool.p) - (long long)J * LD_PAN - J;   // A(r, p) = pan[(r - J) * LD_PAN + (p - J)]
+        CK(cudaMemcpyAsync(d_dfronts.p + 1, &B, sizeof(DFront), cudaMemcpyHostToDevice, stream));
+        HostBatch hb;
+        hb.ids = {1}; hb.f = {B.f}; hb.k = {B.k}; hb.max_k = B.k; hb.dev_off = 0;
+        const int tm = ngt::update_tile_m(opt.gemm_path), tn = ngt::update_tile_n(opt.gemm_path);
+        ngt::LaunchCtx c = ctx(d_pool.p, pool_stride, d_dfronts.p);
+        c.ko = own();
+        const int *ids = d_dids.p + 1;
+        double fl = 0;
+        for (int j = J; j < JE; j += ngt::NB_INNER) {
+            c.ko.wslot = (j - J) / ngt::NB_INNER;
+            const int je = std::min(j + ngt::NB_INNER, JE);
+            ngt::launch_rowpanel(c, ids, 1, j, F0.f + 1 - je);
+            const int tb = max_tiles(hb, j, ngt::MODE_B, tm, tn, fl);
+            if (tb > 0) ngt::launch_update(c, ids, 1, j, ngt::MODE_B, tb, 0);
+            st.n_launches += 2;
+        }
+        const int jl = J + ((kb - 1) / ngt::NB_INNER) * ngt::NB_INNER;
+        const int td = max_tiles(hb, jl, ngt::MODE_D, tm, tn, fl);
+        if (td > 0) ngt::launch_update(c, ids, 1, jl, ngt::MODE_D, td, 0);
+        st.n_launches++;
+        st.schur_flops += fl / dist_G;   // region flops; a rank performs its 1/G share of the columns
+        CK(cudaStreamSynchronize(stream));
+    }
+
+    double *dist_root_contrib() {
+        if (dist_G < 1) throw StateError("ngt_dist_begin has not been called");
+        const ngt::Front &F0 = S.fronts[0];
+        ngt::launch_dist_root_contrib(d_pool.p + F0.off, F0.ld, F0.f, (int)S.nI, m, own(), d_rootc.p, stream);
+        CK(cudaStreamSynchronize(stream));
+        return d_rootc.p;
+    }
+
+    void dist_finish() {
+        if (dist_G < 1) throw StateError("ngt_dist_begin has not been called");
+        const ngt::Front &R = S.fronts[S.root_id];
+        ngt::launch_dist_root_finish(d_pool.p + R.off, R.ld, m, d_rootc.p, d_tauglob.p, (int)S.nI, stream);
+        CK(cudaStreamSynchronize(stream));
+        check_errflag("distributed phase one");
+        have_phase1 = true;
+        have_phase2 = have_backsub = false;
+        last_step_graph = true;   // no per-phase events were recorded for this pass
     }
 
     // committors and MFPTs of every eliminated node by back-substitution (top-down over the assembly tree)
@@ -1281,6 +1439,41 @@ int ngt_profile_schur(ngt_handle h, double *ms_schur, double *flops, int64_t *la
 }
 
 void ngt_trim_device_cache(void) { g_cache.trim(); }
+
+int ngt_dist_begin(ngt_handle h, int32_t rank, int32_t world) {
+    return guard([&] { eng(h)->dist_begin(rank, world); });
+}
+int ngt_dist_rowsum(ngt_handle h, int64_t J, double **dptr, int64_t *ndoubles) {
+    return guard([&] {
+        *dptr = eng(h)->dist_rowsum((int)J);
+        *ndoubles = ngt::NB_OUTER;
+    });
+}
+int ngt_dist_factor(ngt_handle h, int64_t J) {
+    return guard([&] { eng(h)->dist_factor((int)J); });
+}
+int ngt_dist_panel(ngt_handle h, int64_t J, double **dptr, int64_t *ndoubles) {
+    return guard([&] { eng(h)->dist_panel((int)J, dptr, ndoubles); });
+}
+int ngt_dist_apply(ngt_handle h, int64_t J) {
+    return guard([&] { eng(h)->dist_apply((int)J); });
+}
+int ngt_dist_root(ngt_handle h, double **dptr, int64_t *ndoubles) {
+    return guard([&] {
+        Engine *E = eng(h);
+        *dptr = E->dist_root_contrib();
+        *ndoubles = (int64_t)E->m * E->m;
+    });
+}
+int ngt_dist_finish(ngt_handle h) {
+    return guard([&] { eng(h)->dist_finish(); });
+}
+int ngt_dist_info(ngt_handle h, int64_t *n_pivots, int64_t *block) {
+    return guard([&] {
+        *n_pivots = eng(h)->S.nI;
+        *block = ngt::NB_OUTER;
+    });
+}
 
 int ngt_reduced_block_dev(ngt_handle h, double **dptr, int64_t *ndoubles) {
     return guard([&] {

@@ -58,7 +58,7 @@ void launch_rowsum(const LaunchCtx &c, const int *ids, int nfb, int j, int max_c
 // =====================================================================================================
 __global__ void __launch_bounds__(1024, 1)
 panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j,
-             double *wbuf, const double *rsbuf, int maxfb, int maxchunks, int *errflag) {
+             double *wbuf, const double *rsbuf, int maxfb, int maxchunks, int *errflag, KOpt ko) {
     const DFront F = fronts[ids[blockIdx.x]];
     if (j >= F.k) return;
     double *M = pool + (long long)blockIdx.y * pool_stride + F.off;
@@ -130,11 +130,11 @@ panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const in
     __syncthreads();
     const double w = (u < nbp) ? g / Ds[u] : 0.0;
     Ws[u][q] = w;
-    wbuf[((long long)blockIdx.y * maxfb + blockIdx.x) * (NB_INNER * NB_INNER) + u * NB_INNER + q] = w;
+    wbuf[((long long)blockIdx.y * maxfb + blockIdx.x + ko.wslot) * (NB_INNER * NB_INNER) + u * NB_INNER + q] = w;
 
     // fused row panel for narrow fronts: columns je..f (f = tau column) in slabs of 128 staged through smem
     const int ncols = F.f + 1 - je;
-    if (ncols > FUSE_COLS) return;
+    if (ncols > ko.fuse_cols) return;
     const int cc = threadIdx.x & 127, r0 = threadIdx.x >> 7;
     for (int cs = 0; cs < ncols; cs += 128) {
         __syncthreads();
@@ -169,7 +169,7 @@ panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const in
 // =====================================================================================================
 __global__ void __launch_bounds__(256, 4)
 panel_tp_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j,
-                double *wbuf, const double *rsbuf, int maxfb, int maxchunks, int *errflag) {
+                double *wbuf, const double *rsbuf, int maxfb, int maxchunks, int *errflag, KOpt ko) {
     const DFront F = fronts[ids[blockIdx.x]];
     if (j >= F.k) return;
     double *M = pool + (long long)blockIdx.y * pool_stride + F.off;
@@ -264,7 +264,7 @@ panel_tp_kernel(double *pool, long long pool_stride, const DFront *fronts, const
         }
     }
     __syncthreads();
-    double *Wout = wbuf + ((long long)blockIdx.y * maxfb + blockIdx.x) * (NB_INNER * NB_INNER);
+    double *Wout = wbuf + ((long long)blockIdx.y * maxfb + blockIdx.x + ko.wslot) * (NB_INNER * NB_INNER);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const double w = (u < nbp) ? g[e] / Ds[u] : 0.0;
@@ -272,7 +272,7 @@ panel_tp_kernel(double *pool, long long pool_stride, const DFront *fronts, const
         Wout[u * NB_INNER + q0 + e] = w;
     }
     const int ncols = F.f + 1 - je;
-    if (ncols > FUSE_COLS) return;
+    if (ncols > ko.fuse_cols) return;
     const int cc = threadIdx.x & 63, r0 = threadIdx.x >> 6;
     for (int cs = 0; cs < ncols; cs += 64) {
         __syncthreads();
@@ -304,10 +304,10 @@ void launch_panel(const LaunchCtx &c, const int *ids, int nfb, int j) {
     dim3 grid(nfb, c.nbatch);
     if ((long long)nfb * c.nbatch >= 2 * 148)   // many panels: favour occupancy over single-panel latency
         panel_tp_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.rsbuf, c.maxfb,
-                                                   c.maxchunks, c.errflag);
+                                                   c.maxchunks, c.errflag, c.ko);
     else
         panel_kernel<<<grid, 1024, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.rsbuf, c.maxfb,
-                                                 c.maxchunks, c.errflag);
+                                                 c.maxchunks, c.errflag, c.ko);
 }
 
 // =====================================================================================================
@@ -316,22 +316,22 @@ void launch_panel(const LaunchCtx &c, const int *ids, int nfb, int j) {
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
 rowpanel_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j,
-                const double *wbuf, int maxfb) {
+                const double *wbuf, int maxfb, KOpt ko) {
     const DFront F = fronts[ids[blockIdx.y]];
     if (j >= F.k) return;
     const int nbp = min(NB_INNER, F.k - j);
     const int je = j + nbp;
-    if (F.f + 1 - je <= FUSE_COLS) return;       // done inside the panel kernel
+    if (F.f + 1 - je <= ko.fuse_cols) return;    // done inside the panel kernel
     const int col = je + blockIdx.x * 128 + (threadIdx.x & 127);
     if (je + (int)blockIdx.x * 128 > F.f) return;
     double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
 
     __shared__ double Ws[NB_INNER][NB_INNER];
-    const double *W = wbuf + ((long long)blockIdx.z * maxfb + blockIdx.y) * (NB_INNER * NB_INNER);
+    const double *W = wbuf + ((long long)blockIdx.z * maxfb + blockIdx.y + ko.wslot) * (NB_INNER * NB_INNER);
     for (int i = threadIdx.x; i < NB_INNER * NB_INNER; i += 256) Ws[i / NB_INNER][i % NB_INNER] = W[i];
 
     double x[NB_INNER];
-    const bool live = col <= F.f;
+    const bool live = col <= F.f && owned_col(ko, col, F.f);
 #pragma unroll
     for (int r = 0; r < NB_INNER; ++r) x[r] = (live && r < nbp) ? M[(long long)(j + r) * F.ld + col] : 0.0;
     __syncthreads();
@@ -352,7 +352,7 @@ rowpanel_kernel(double *pool, long long pool_stride, const DFront *fronts, const
 void launch_rowpanel(const LaunchCtx &c, const int *ids, int nfb, int j, int max_cols) {
     dim3 grid((max_cols + 127) / 128, nfb, c.nbatch);
     if (grid.x == 0) grid.x = 1;
-    rowpanel_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.maxfb);
+    rowpanel_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.maxfb, c.ko);
 }
 
 // =====================================================================================================
@@ -363,7 +363,7 @@ constexpr int FT = 64, FK = 16;
 
 __global__ void __launch_bounds__(256)
 update_dfma_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode_in,
-                   int split) {
+                   int split, KOpt ko) {
     const DFront F = fronts[ids[blockIdx.y]];
     Region R;
     int mode = mode_in, tile = blockIdx.x;
@@ -372,13 +372,16 @@ update_dfma_kernel(double *pool, long long pool_stride, const DFront *fronts, co
     } else if (mode_in == MODE_D1) {
         if (tile < split) mode = MODE_D1A; else { mode = MODE_D1B; tile -= split; }
     }
-    if (!get_region(F.f, F.k, j, mode, R)) return;
+    if (!get_region(F.f, F.fr, F.k, j, mode, R)) return;
     const int tiles_c = (R.c1 - R.c0 + FT - 1) / FT;
     const int tiles_r = (R.r1 - R.r0 + FT - 1) / FT;
     const int tr = tile / tiles_c, tc = tile % tiles_c;
     if (tr >= tiles_r) return;
     double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
+    const double *MA = F.a_ld ? pool + (long long)blockIdx.z * pool_stride + F.a_off : M;
+    const long long lda = F.a_ld ? F.a_ld : F.ld;
     const int rb = R.r0 + tr * FT, cb = R.c0 + tc * FT;
+    if (ko.own_G > 1 && !owned_col(ko, cb, F.f) && !owned_col(ko, min(cb + FT, R.c1) - 1, F.f)) return;
 
     __shared__ double As[FT][FK + 1];
     __shared__ double Bs[FK][FT + 1];
@@ -392,7 +395,7 @@ update_dfma_kernel(double *pool, long long pool_stride, const DFront *fronts, co
     for (int kb = R.k0; kb < R.k1; kb += FK) {
         for (int i = threadIdx.x; i < FT * FK; i += 256) {
             const int r = i / FK, kk = i % FK;
-            As[r][kk] = (rb + r < R.r1 && kb + kk < R.k1) ? M[(long long)(rb + r) * F.ld + kb + kk] : 0.0;
+            As[r][kk] = (rb + r < R.r1 && kb + kk < R.k1) ? MA[(long long)(rb + r) * lda + kb + kk] : 0.0;
         }
         for (int i = threadIdx.x; i < FK * FT; i += 256) {
             const int kk = i / FT, cc = i % FT;
@@ -418,7 +421,7 @@ update_dfma_kernel(double *pool, long long pool_stride, const DFront *fronts, co
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
             const int cidx = cb + tx + 16 * y;
-            if (cidx < R.c1) M[(long long)r * F.ld + cidx] += acc[x][y];
+            if (cidx < R.c1 && owned_col(ko, cidx, F.f)) M[(long long)r * F.ld + cidx] += acc[x][y];
         }
     }
 }
@@ -450,7 +453,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 __global__ void __launch_bounds__(256, 2)
 update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode_in,
-                   int split) {
+                   int split, KOpt ko) {
     const DFront F = fronts[ids[blockIdx.y]];
     Region R;
     int mode = mode_in, tile = blockIdx.x;
@@ -459,14 +462,17 @@ update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, co
     } else if (mode_in == MODE_D1) {
         if (tile < split) mode = MODE_D1A; else { mode = MODE_D1B; tile -= split; }
     }
-    if (!get_region(F.f, F.k, j, mode, R)) return;
+    if (!get_region(F.f, F.fr, F.k, j, mode, R)) return;
     const int tiles_c = (R.c1 - R.c0 + TN - 1) / TN;
     const int tiles_r = (R.r1 - R.r0 + TM - 1) / TM;
     const int tr = tile / tiles_c, tc = tile % tiles_c;
     if (tr >= tiles_r) return;
     double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
+    const double *MA = F.a_ld ? pool + (long long)blockIdx.z * pool_stride + F.a_off : M;
+    const long long lda = F.a_ld ? F.a_ld : F.ld;
     const int rb = R.r0 + tr * TM, cb = R.c0 + tc * TN;
     const long long ld = F.ld;
+    if (ko.own_G > 1 && !owned_col(ko, cb, F.f) && !owned_col(ko, min(cb + TN, R.c1) - 1, F.f)) return;
 
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -491,7 +497,7 @@ update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, co
     // per-thread load slots: A element (row ar + 16 i, pivot kb + ak), B element (pivot kb + bk + 4 i, column bc)
     const int ar = threadIdx.x >> 4, ak = threadIdx.x & 15;
     const int bk = threadIdx.x >> 6, bc = threadIdx.x & 63;
-    const double *pa = M + (long long)(rb + ar) * ld + ak;
+    const double *pa = MA + (long long)(rb + ar) * lda + ak;
     const double *pb = M + (long long)bk * ld + cb + bc;
     unsigned amask = 0;
 #pragma unroll
@@ -504,7 +510,7 @@ update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, co
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const bool ok = ka && ((amask >> i) & 1u);
-            cp_async8(sa + stg * TSTAGE_DOUBLES + i * 16 * AS_LD, ok ? pa + (long long)i * 16 * ld + kb : M, ok);
+            cp_async8(sa + stg * TSTAGE_DOUBLES + i * 16 * AS_LD, ok ? pa + (long long)i * 16 * lda + kb : M, ok);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -548,8 +554,8 @@ update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, co
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
             const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
-            if (c0 < R.c1) row[c0] = acc[mi][ni][0];
-            if (c0 + 1 < R.c1) row[c0 + 1] = acc[mi][ni][1];
+            if (c0 < R.c1 && owned_col(ko, c0, F.f)) row[c0] = acc[mi][ni][0];
+            if (c0 + 1 < R.c1 && owned_col(ko, c0 + 1, F.f)) row[c0 + 1] = acc[mi][ni][1];
         }
     }
 }
@@ -566,7 +572,7 @@ constexpr int STAGE_DOUBLES = BM * BA_LD + BK * BB_LD;
 
 __global__ void __launch_bounds__(512, 1)
 update_dmma_big_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode_in,
-                       int split) {
+                       int split, KOpt ko) {
     const DFront F = fronts[ids[blockIdx.y]];
     Region R;
     int mode = mode_in, tile = blockIdx.x;
@@ -575,14 +581,17 @@ update_dmma_big_kernel(double *pool, long long pool_stride, const DFront *fronts
     } else if (mode_in == MODE_D1) {
         if (tile < split) mode = MODE_D1A; else { mode = MODE_D1B; tile -= split; }
     }
-    if (!get_region(F.f, F.k, j, mode, R)) return;
+    if (!get_region(F.f, F.fr, F.k, j, mode, R)) return;
     const int tiles_c = (R.c1 - R.c0 + BN - 1) / BN;
     const int tiles_r = (R.r1 - R.r0 + BM - 1) / BM;
     const int tr = tile / tiles_c, tc = tile % tiles_c;
     if (tr >= tiles_r) return;
     double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
+    const double *MA = F.a_ld ? pool + (long long)blockIdx.z * pool_stride + F.a_off : M;
+    const long long lda = F.a_ld ? F.a_ld : F.ld;
     const int rb = R.r0 + tr * BM, cb = R.c0 + tc * BN;
     const long long ld = F.ld;
+    if (ko.own_G > 1 && !owned_col(ko, cb, F.f) && !owned_col(ko, min(cb + BN, R.c1) - 1, F.f)) return;
 
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -607,7 +616,7 @@ update_dmma_big_kernel(double *pool, long long pool_stride, const DFront *fronts
     // per-thread load slots: A element (row ar + 32 i, pivot kb + ak), B element (pivot kb + bk + 4 i, column bc)
     const int ar = threadIdx.x >> 4, ak = threadIdx.x & 15;
     const int bk = threadIdx.x >> 7, bc = threadIdx.x & 127;
-    const double *pa = M + (long long)(rb + ar) * ld + ak;
+    const double *pa = MA + (long long)(rb + ar) * lda + ak;
     const double *pb = M + (long long)bk * ld + cb + bc;
     unsigned amask = 0;
 #pragma unroll
@@ -620,7 +629,7 @@ update_dmma_big_kernel(double *pool, long long pool_stride, const DFront *fronts
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const bool ok = ka && ((amask >> i) & 1u);
-            cp_async8(sa + stg * STAGE_DOUBLES + i * 32 * BA_LD, ok ? pa + (long long)i * 32 * ld + kb : M, ok);
+            cp_async8(sa + stg * STAGE_DOUBLES + i * 32 * BA_LD, ok ? pa + (long long)i * 32 * lda + kb : M, ok);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -663,8 +672,8 @@ update_dmma_big_kernel(double *pool, long long pool_stride, const DFront *fronts
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
             const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
-            if (c0 < R.c1) row[c0] = acc[mi][ni][0];
-            if (c0 + 1 < R.c1) row[c0 + 1] = acc[mi][ni][1];
+            if (c0 < R.c1 && owned_col(ko, c0, F.f)) row[c0] = acc[mi][ni][0];
+            if (c0 + 1 < R.c1 && owned_col(ko, c0 + 1, F.f)) row[c0 + 1] = acc[mi][ni][1];
         }
     }
 }
@@ -683,13 +692,13 @@ void launch_update(const LaunchCtx &c, const int *ids, int nfb, int j, int mode,
     if (max_tiles <= 0) return;
     dim3 grid(max_tiles, nfb, c.nbatch);
     if (c.gemm_path == 1) {
-        update_dfma_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split);
+        update_dfma_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split, c.ko);
     } else if (c.gemm_path == 2) {
         const size_t smem = (size_t)STG * STAGE_DOUBLES * sizeof(double);
-        update_dmma_big_kernel<<<grid, 512, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split);
+        update_dmma_big_kernel<<<grid, 512, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split, c.ko);
     } else {
         const size_t smem = (size_t)TSTG * TSTAGE_DOUBLES * sizeof(double);
-        update_dmma_kernel<<<grid, 256, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split);
+        update_dmma_kernel<<<grid, 256, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split, c.ko);
     }
 }
 
@@ -882,6 +891,92 @@ void launch_phase2_collect(const LaunchCtx &c, const double *p2pool, long long p
     dim3 grid((ntask + 127) / 128, c.nbatch);
     phase2_collect_kernel<<<grid, 128, 0, c.stream>>>(p2pool, p2_stride, p2fronts, task0, ntask, ng, om, tau,
                                                      out_stride, out_off, rank, nranks);
+}
+
+// =====================================================================================================
+// multi-GPU dense path (1-D block-cyclic columns): helper kernels.  Every rank holds the whole
+// matrix but only keeps its own column blocks (width NB_OUTER) up to date; the outer block being eliminated travels
+// as a rectangular "panel front" (rows J.., its NB_OUTER columns, one column S with the mass outside the block, tau).
+// =====================================================================================================
+// partial S_r = sum over OWNED columns c in [JE, f) of P[J + r, c]; one CTA per row
+__global__ void __launch_bounds__(256)
+dist_rowsum_kernel(const double *M, int ld, int f, int J, int JE, KOpt ko, double *out) {
+    const int r = blockIdx.x;
+    const double *row = M + (long long)(J + r) * ld;
+    double s = 0.0;
+    for (int c = JE + threadIdx.x; c < f; c += 256)
+        if (owned_col(ko, c, f)) s += row[c];
+    s = warp_sum(s);
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) out[r] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+}
+
+// owner: panel front <- column panel of the big matrix + S + tau
+__global__ void __launch_bounds__(128)
+dist_pack_kernel(const double *M, int ld, int J, int kb, int fr, double *pan, int ld_pan, const double *S,
+                 const double *tau_glob) {
+    const int r = blockIdx.x;
+    if (r >= fr) return;
+    const double *row = M + (long long)(J + r) * ld + J;
+    double *dst = pan + (long long)r * ld_pan;
+    for (int c = threadIdx.x; c < ld_pan; c += 128) {
+        double v = 0.0;
+        if (c < kb) v = row[c];
+        else if (c == kb) v = (r < kb) ? S[r] : 0.0;
+        else if (c == kb + 1) v = tau_glob[J + r];
+        dst[c] = v;
+    }
+}
+
+// everybody, after the broadcast: the panel's tau column is the new tau of rows J..
+__global__ void dist_tau_kernel(const double *pan, int ld_pan, int kb, int fr, int J, double *tau_glob) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < fr) tau_glob[J + r] = pan[(long long)r * ld_pan + kb + 1];
+}
+
+__global__ void dist_tau_init_kernel(const double *tau0, const int *pos, int n, double *tau_glob) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < n) tau_glob[pos[u]] = tau0[u];
+}
+
+// contributions of this rank's columns to the reduced A ∪ B block (others zero; summed with one all-reduce)
+__global__ void dist_root_contrib_kernel(const double *M, int ld, int f, int nI, int m, KOpt ko, double *out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * m) return;
+    const int i = idx / m, jx = idx % m;
+    out[idx] = owned_col(ko, nI + jx, f) ? M[(long long)(nI + i) * ld + nI + jx] : 0.0;
+}
+
+__global__ void dist_root_finish_kernel(double *root, int ld_root, int m, const double *contrib, const double *tau_glob,
+                                        int nI) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * (m + 1)) return;
+    const int i = idx / (m + 1), jx = idx % (m + 1);
+    if (jx < m) root[(long long)i * ld_root + jx] += contrib[i * m + jx];
+    else root[(long long)i * ld_root + m] = tau_glob[nI + i];
+}
+
+void launch_dist_rowsum(const double *M, int ld, int f, int J, int JE, KOpt ko, double *out, cudaStream_t s) {
+    dist_rowsum_kernel<<<JE - J, 256, 0, s>>>(M, ld, f, J, JE, ko, out);
+}
+void launch_dist_pack(const double *M, int ld, int J, int kb, int fr, double *pan, int ld_pan, const double *S,
+                      const double *tau_glob, cudaStream_t s) {
+    dist_pack_kernel<<<fr, 128, 0, s>>>(M, ld, J, kb, fr, pan, ld_pan, S, tau_glob);
+}
+void launch_dist_tau(const double *pan, int ld_pan, int kb, int fr, int J, double *tau_glob, cudaStream_t s) {
+    dist_tau_kernel<<<(fr + 255) / 256, 256, 0, s>>>(pan, ld_pan, kb, fr, J, tau_glob);
+}
+void launch_dist_tau_init(const double *tau0, const int *pos, int n, double *tau_glob, cudaStream_t s) {
+    dist_tau_init_kernel<<<(n + 255) / 256, 256, 0, s>>>(tau0, pos, n, tau_glob);
+}
+void launch_dist_root_contrib(const double *M, int ld, int f, int nI, int m, KOpt ko, double *out, cudaStream_t s) {
+    dist_root_contrib_kernel<<<(m * m + 255) / 256, 256, 0, s>>>(M, ld, f, nI, m, ko, out);
+}
+void launch_dist_root_finish(double *root, int ld_root, int m, const double *contrib, const double *tau_glob, int nI,
+                             cudaStream_t s) {
+    dist_root_finish_kernel<<<(m * (m + 1) + 255) / 256, 256, 0, s>>>(root, ld_root, m, contrib, tau_glob, nI);
 }
 
 // =====================================================================================================

@@ -31,8 +31,20 @@ constexpr int NB_OUTER = NGT_NB_OUTER;   // pivots per delayed trailing update (
 
 struct DFront {
     long long off;   // offset in the pool (doubles)
-    int f, k, ld;    // order, pivots, leading dimension
+    int f, k, ld;    // order (columns; column f is tau), pivots, leading dimension
     int parent;      // front id or -1
+    // Optional generalisations used by the multi-GPU dense path (0 = not used):
+    int fr;          // number of rows when the front is rectangular (panel fronts); 0 -> f
+    int a_ld;        // leading dimension of a separate A-operand matrix for the Schur updates; 0 -> A is this front
+    long long a_off; // its pool offset, pre-shifted so that A(r, p) = pool[a_off + r*a_ld + p] in this front's indices
+};
+
+// per-launch options that only the multi-GPU dense path changes
+struct KOpt {
+    int own_G;       // column ownership: column c is owned iff ((c / NB_OUTER) % own_G) == own_g; 0 or 1 -> all owned
+    int own_g;
+    int wslot;       // slot offset into wbuf (one W per inner panel of an outer block)
+    int fuse_cols;   // row-panel fusion threshold (FUSE_COLS; 0 forces the stand-alone row-panel kernel)
 };
 
 constexpr int RS_CHUNK = 512;   // columns per partial-row-sum CTA (one warp per panel row)
@@ -52,21 +64,27 @@ struct Region { int r0, r1, c0, c1, k0, k1; };
 //   MODE_B: row panel of the remaining outer pivots  rows [je,JE) cols [JE,f]    K = [j,je)
 //   MODE_D: delayed trailing update                  rows [JE,f)  cols [JE,f]    K = [J,JE)
 // column f is the tau column, so "cols [..,f]" means c1 = f+1.
-__host__ __device__ inline bool get_region(int f, int k, int j, int mode, Region &R) {
+__host__ __device__ inline bool owned_col(const KOpt &o, int c, int f) {
+    if (o.own_G <= 1) return true;
+    return c < f && ((c / NB_OUTER) % o.own_G) == o.own_g;     // the tau column of the big matrix is not used there
+}
+
+__host__ __device__ inline bool get_region(int f, int fr, int k, int j, int mode, Region &R) {
+    if (fr <= 0) fr = f;
     if (j >= k) return false;
     const int je = (j + NB_INNER < k ? j + NB_INNER : k);
     const int J = (j / NB_OUTER) * NB_OUTER;
     const int JE = (J + NB_OUTER < k ? J + NB_OUTER : k);
-    if (mode == MODE_A) { R.r0 = je; R.r1 = f; R.c0 = je; R.c1 = JE; R.k0 = j; R.k1 = je; }
-    else if (mode == MODE_B) { R.r0 = je; R.r1 = JE; R.c0 = JE; R.c1 = f + 1; R.k0 = j; R.k1 = je; }
+    if (mode == MODE_A) { R.r0 = je; R.r1 = fr; R.c0 = je; R.c1 = JE; R.k0 = j; R.k1 = je; }
+    else if (mode == MODE_B) { R.r0 = je; R.r1 = (JE < fr ? JE : fr); R.c0 = JE; R.c1 = f + 1; R.k0 = j; R.k1 = je; }
     else {
         if (je != JE) return false;   // delayed updates run once, after the last panel of the outer block
         const int JE2 = (JE + NB_OUTER < k ? JE + NB_OUTER : k);
         R.k0 = J; R.k1 = JE;
-        if (mode == MODE_D) { R.r0 = JE; R.r1 = f; R.c0 = JE; R.c1 = f + 1; }
-        else if (mode == MODE_D1A) { R.r0 = JE; R.r1 = f; R.c0 = JE; R.c1 = JE2; }
-        else if (mode == MODE_D1B) { R.r0 = JE; R.r1 = JE2; R.c0 = JE2; R.c1 = f + 1; }
-        else { R.r0 = JE2; R.r1 = f; R.c0 = JE2; R.c1 = f + 1; }
+        if (mode == MODE_D) { R.r0 = JE; R.r1 = fr; R.c0 = JE; R.c1 = f + 1; }
+        else if (mode == MODE_D1A) { R.r0 = JE; R.r1 = fr; R.c0 = JE; R.c1 = JE2; }
+        else if (mode == MODE_D1B) { R.r0 = JE; R.r1 = (JE2 < fr ? JE2 : fr); R.c0 = JE2; R.c1 = f + 1; }
+        else { R.r0 = JE2; R.r1 = fr; R.c0 = JE2; R.c1 = f + 1; }
     }
     return R.r1 > R.r0 && R.c1 > R.c0;
 }
@@ -84,6 +102,7 @@ struct LaunchCtx {
     int *errflag;             // device int
     cudaStream_t stream;
     int gemm_path;            // 0 DMMA, 1 DFMA
+    KOpt ko;                  // {0,0,0,FUSE_COLS} outside the multi-GPU dense path
 };
 
 // ids: device array of front ids in this batch (nfb of them).
@@ -127,6 +146,16 @@ void launch_phase2_gather(const LaunchCtx &c, DFront root, int g0, int ng, int o
 void launch_phase2_collect(const LaunchCtx &c, const double *p2pool, long long p2_stride, const DFront *p2fronts,
                            int task0, int ntask, int ng, double *om, double *tau, int out_stride, int out_off,
                            int rank, int nranks);
+
+// ---- multi-GPU dense path helpers (see kernels.cu) --------------------------------------------------------
+void launch_dist_rowsum(const double *M, int ld, int f, int J, int JE, KOpt ko, double *out, cudaStream_t s);
+void launch_dist_pack(const double *M, int ld, int J, int kb, int fr, double *pan, int ld_pan, const double *S,
+                      const double *tau_glob, cudaStream_t s);
+void launch_dist_tau(const double *pan, int ld_pan, int kb, int fr, int J, double *tau_glob, cudaStream_t s);
+void launch_dist_tau_init(const double *tau0, const int *pos, int n, double *tau_glob, cudaStream_t s);
+void launch_dist_root_contrib(const double *M, int ld, int f, int nI, int m, KOpt ko, double *out, cudaStream_t s);
+void launch_dist_root_finish(double *root, int ld_root, int m, const double *contrib, const double *tau_glob, int nI,
+                             cudaStream_t s);
 
 // ---- committor / MFPT back-substitution over kept factors -------------------------------------------
 // x is nbatch x npos x 2 (q, t interleaved) indexed by elimination position; one call handles the panel that

@@ -298,7 +298,11 @@ void finish_layout(Symbolic &S) {
         }
     }
 
-    // batches: per level, fronts with pivots, grouped by size class (within 2x) and capped for gridDim.y
+    // batches: per level, fronts with pivots, grouped by size class and capped for gridDim.y.  Fronts of one batch
+    // share every launch, so the panel chains of same-level fronts run side by side; a wide class ratio keeps the
+    // number of sequential chains per level small (grids are sized by the largest front, smaller ones exit early).
+    int size_class_ratio = 8;
+    if (const char *e = std::getenv("NGT_B200_CLASS_RATIO")) size_class_ratio = std::max(1, std::atoi(e));
     S.batches.clear();
     std::vector<std::vector<int32_t> > by_level(S.n_levels);
     for (int32_t i = 0; i < nf; ++i)
@@ -316,7 +320,7 @@ void finish_layout(Symbolic &S) {
             b.max_f = S.fronts[v[i]].f;
             b.max_k = 0;
             size_t j = i;
-            while (j < v.size() && j - i < 32768 && S.fronts[v[j]].f * 2 >= b.max_f) {
+            while (j < v.size() && j - i < 32768 && S.fronts[v[j]].f * size_class_ratio >= b.max_f) {
                 b.max_k = std::max(b.max_k, S.fronts[v[j]].k);
                 b.fronts.push_back(v[j]);
                 ++j;

@@ -82,3 +82,71 @@ def gather_rates(local_rates, n_total, rank, world, group=None):
     full = np.zeros((n_total,) + local_rates.shape[1:])
     full[lo:hi] = local_rates
     return all_reduce_sum(full, group)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# One dense network over several GPUs (BASELINE config 3 at N > 1): 1-D block-cyclic columns + panel broadcast.
+# The engine exposes the per-block stages (include/ngt_b200.h, ngt_dist_*); the collectives are issued here.
+# ---------------------------------------------------------------------------------------------------------------
+def _dev_tensor(ptr, n):
+    import torch
+    return torch.as_tensor(_DeviceBlock(ptr, n), device="cuda")
+
+
+def dense_phase_one_distributed(handle, group=None):
+    """Phase 1 of one complete network spread over the ranks of `group` (every rank holds a handle created from the
+    same rate matrix).  Per outer block: all-reduce of the block rows' outside mass (for the subtraction-free
+    pivots), panel factorisation on the owning rank, NCCL broadcast of the factored panel, trailing update of the
+    own columns on every rank.  Afterwards handle.phase_two() / rates() work as usual on every rank."""
+    import torch
+    dist = _dist()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    handle.dist_begin(rank, world)
+    npiv, block = handle.dist_info()
+    for J in range(0, npiv, block):
+        p, n = handle.dist_rowsum(J)
+        dist.all_reduce(_dev_tensor(p, n), op=dist.ReduceOp.SUM, group=group)
+        torch.cuda.synchronize()      # the engine works on its own streams: the collective must have landed
+        owner = (J // block) % world
+        if rank == owner:
+            handle.dist_factor(J)
+        p, n = handle.dist_panel(J)
+        dist.broadcast(_dev_tensor(p, n), src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+        torch.cuda.synchronize()
+        handle.dist_apply(J)
+    p, n = handle.dist_root()
+    dist.all_reduce(_dev_tensor(p, n), op=dist.ReduceOp.SUM, group=group)
+    torch.cuda.synchronize()
+    handle.dist_finish()
+
+
+def dense_phase_one_emulated(handles):
+    """The same schedule with the ranks emulated by `handles` inside ONE process on ONE GPU (tests): the collectives
+    become explicit sums / copies between the handles' device buffers."""
+    import torch
+    world = len(handles)
+    for g, h in enumerate(handles):
+        h.dist_begin(g, world)
+    npiv, block = handles[0].dist_info()
+    for J in range(0, npiv, block):
+        parts = [_dev_tensor(*h.dist_rowsum(J)) for h in handles]
+        total = torch.stack(parts).sum(0)
+        for t in parts:
+            t.copy_(total)
+        torch.cuda.synchronize()
+        owner = (J // block) % world
+        handles[owner].dist_factor(J)
+        src = _dev_tensor(*handles[owner].dist_panel(J))
+        for g, h in enumerate(handles):
+            if g != owner:
+                _dev_tensor(*h.dist_panel(J)).copy_(src)
+        torch.cuda.synchronize()
+        for h in handles:
+            h.dist_apply(J)
+    parts = [_dev_tensor(*h.dist_root()) for h in handles]
+    total = torch.stack(parts).sum(0)
+    for t in parts:
+        t.copy_(total)
+    torch.cuda.synchronize()
+    for h in handles:
+        h.dist_finish()

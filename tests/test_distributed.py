@@ -107,3 +107,34 @@ def test_phase_two_shards_merge_to_the_unsharded_result():
     others = np.sum(parts[1:], axis=0)
     phase_two_sharded(h, 0, world, lambda a: a + others)
     assert np.allclose(h.rates(), ref.rates(), rtol=1e-15, atol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,world,nA,nB", [(300, 1, 1, 1), (300, 2, 1, 1), (700, 3, 2, 3), (1100, 4, 1, 1), (515, 2, 1, 1)])
+def test_dense_network_over_emulated_ranks_matches_single_gpu(n, world, nA, nB):
+    """1-D block-cyclic dense elimination with panel hand-over (BASELINE config 3 at N > 1), ranks emulated one after
+    the other on one GPU through the ngt_dist_* C ABI; must agree with the single-GPU path and the CPU oracle."""
+    import torch
+    from kmc_rates_b200 import synth
+    from kmc_rates_b200._capi import Handle
+    from kmc_rates_b200.distributed import dense_phase_one_emulated
+    from oracle.cpu_ngt import CpuNGT
+    src, dst, k = synth.complete_random(n, seed=n)
+    K = np.zeros((n, n))
+    K[src, dst] = k
+    A, B = list(range(nA)), list(range(n - nB, n))
+    Kd = torch.from_numpy(K).cuda()
+    ref = Handle.from_dense(Kd, A, B)
+    ref.compute_rates()
+    handles = [Handle.from_dense(Kd, A, B) for _ in range(world)]
+    dense_phase_one_emulated(handles)
+    for h in handles:
+        h.phase_two()
+        assert np.allclose(h.rates(), ref.rates(), rtol=1e-11, atol=0)
+        P, t = h.reduced()
+        Pr, tr = ref.reduced()
+        assert np.allclose(P, Pr, rtol=1e-11, atol=1e-300) and np.allclose(t, tr, rtol=1e-11, atol=0)
+    if n <= 700:
+        cpu = CpuNGT(n, src, dst, k, A, B, kind="port")
+        cpu.compute_rates()
+        assert np.allclose(handles[0].rates(), cpu.rates(), rtol=1e-9, atol=0)
