@@ -213,6 +213,19 @@ struct Engine {
 
     bool use_big_kernel = std::getenv("NGT_B200_BIG") != nullptr;   // 128 x 128 kernel: measured slower than 2 CTAs/SM of 128 x 64
     bool use_lookahead = std::getenv("NGT_B200_NO_LOOKAHEAD") == nullptr;
+    // Bulk-copy (TMA, cp.async.bulk + mbarrier) fed variant of the Schur kernel: correct, but with one 128-byte bulk
+    // copy per tile row it measured 3x SLOWER than the cp.async ring (dense 16 384: 343 ms vs 117 ms per step) — the
+    // copy engine wants KB-sized boxes.  Opt-in (NGT_B200_TMA=1) until the 2-D tensor-map version replaces it.
+    bool use_tma = std::getenv("NGT_B200_TMA") != nullptr;
+
+    // cp.async.bulk needs 16-byte aligned global addresses and sizes: K a multiple of the 16-pivot stage and starting
+    // on one, tile columns starting on an even index (rows start 64-byte aligned by construction: ld % 8 == 0)
+    static bool tma_eligible(const HostBatch &b, size_t i, int j, int mode) {
+        ngt::Region R;
+        if (!ngt::get_region(b.f[i], b.fr.empty() ? 0 : b.fr[i], b.k[i], j, mode, R)) return false;
+        const int tk = ngt::update_tile_k();
+        return (R.k1 - R.k0) % tk == 0 && R.k0 % tk == 0 && R.c0 % 2 == 0 && (R.k1 - R.k0) >= 4 * tk;
+    }
     bool use_graph = std::getenv("NGT_B200_NO_GRAPH") == nullptr;
     bool capturing = false, last_step_graph = false;
     long long steps_done = 0;
@@ -516,6 +529,9 @@ struct Engine {
                     c2.gemm_path = 2;
                     td2 = tbig;
                 }
+                // single-front trailing updates whose operands meet the bulk-copy alignment rules are fed by TMA
+                if (opt.gemm_path == 0 && use_tma && c2.gemm_path == 0 && nfb == 1 && tma_eligible(b, 0, j, ngt::MODE_D2))
+                    c2.gemm_path = 3;
                 // look-ahead: a trailing update big enough to keep the GPU busy runs on the second stream while
                 // the next outer block's panels proceed on the main stream
                 d2_async = use_lookahead && (long long)td2 * live * nbatch >= 148;

@@ -561,6 +561,144 @@ update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, co
 }
 
 // =====================================================================================================
+// Schur update fed by the bulk-copy engine (TMA, `cp.async.bulk` -> SASS UBLKCP) with mbarrier hand-over:
+// warp 8 is the producer (it arms the stage's "full" mbarrier with the byte count and issues one bulk copy per tile
+// row: 128 B of A per row, up to 512 B of B per pivot), warps 0-7 are the consumers (wait on "full", LDS + DMMA,
+// arrive on "empty").  No thread of the math warps touches addresses or predicates of the global loads.
+// Same tile geometry, shared-memory layout and accumulation order as update_dmma_kernel, so results are bitwise
+// equal.  Used for single-front trailing updates whose operands satisfy the 16-byte alignment rules of bulk
+// copies (full outer blocks; the host checks, see Engine::tma_eligible); everything else stays on cp.async.
+// =====================================================================================================
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int TMA_THREADS = 288;   // 8 math warps + 1 producer warp
+
+__global__ void __maxnreg__(112)
+update_dmma_tma_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode_in,
+                       int split, KOpt ko) {
+    const DFront F = fronts[ids[blockIdx.y]];
+    Region R;
+    int mode = mode_in, tile = blockIdx.x;
+    if (mode_in == MODE_AB) {
+        if (tile < split) mode = MODE_A; else { mode = MODE_B; tile -= split; }
+    } else if (mode_in == MODE_D1) {
+        if (tile < split) mode = MODE_D1A; else { mode = MODE_D1B; tile -= split; }
+    }
+    if (!get_region(F.f, F.fr, F.k, j, mode, R)) return;
+    const int tiles_c = (R.c1 - R.c0 + TN - 1) / TN;
+    const int tiles_r = (R.r1 - R.r0 + TM - 1) / TM;
+    const int tr = tile / tiles_c, tc = tile % tiles_c;
+    if (tr >= tiles_r) return;
+    double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
+    const double *MA = F.a_ld ? pool + (long long)blockIdx.z * pool_stride + F.a_off : M;
+    const long long lda = F.a_ld ? F.a_ld : F.ld;
+    const int rb = R.r0 + tr * TM, cb = R.c0 + tc * TN;
+    const long long ld = F.ld;
+    if (ko.own_G > 1 && !owned_col(ko, cb, F.f) && !owned_col(ko, min(cb + TN, R.c1) - 1, F.f)) return;
+
+    extern __shared__ double smem[];
+    __shared__ unsigned long long full_bar[TSTG], empty_bar[TSTG];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < TSTG; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nk = (R.k1 - R.k0) / TK;                      // host guarantees K % 16 == 0
+    const int arows = min(TM, R.r1 - rb);                   // tile rows that exist
+    const int bcols = min(TN, ((R.c1 - cb) + 1) & ~1);      // even count; row padding (ld >= f+1 rounded to 8) covers it
+    const unsigned stage_bytes = (unsigned)(arows * TK * 8 + TK * bcols * 8);
+
+    if (warp == 8) {
+        // ===== producer =====
+        for (int kt = 0; kt < nk; ++kt) {
+            const int stg = kt % TSTG;
+            if (kt >= TSTG) mbar_wait(&empty_bar[stg], ((kt / TSTG) - 1) & 1);
+            const int kb = R.k0 + kt * TK;
+            double *As = smem + stg * TSTAGE_DOUBLES;
+            double *Bs = As + TM * AS_LD;
+            if (lane == 0) mbar_expect_tx(&full_bar[stg], stage_bytes);
+            __syncwarp();
+            for (int r = lane; r < arows; r += 32)
+                bulk_g2s(As + r * AS_LD, MA + (long long)(rb + r) * lda + kb, TK * 8, &full_bar[stg]);
+            if (lane < TK)
+                bulk_g2s(Bs + lane * BS_LD, M + (long long)(kb + lane) * ld + cb, bcols * 8, &full_bar[stg]);
+        }
+        return;
+    }
+    // ===== consumers =====
+    const int wm = warp & 3, wn = warp >> 2;
+    const int g = lane >> 2, t4 = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        const int r = rb + wm * 32 + mi * 8 + g;
+        const double *row = M + (long long)r * ld;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
+            acc[mi][ni][0] = (r < R.r1 && c0 < R.c1) ? row[c0] : 0.0;
+            acc[mi][ni][1] = (r < R.r1 && c0 + 1 < R.c1) ? row[c0 + 1] : 0.0;
+        }
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        const int stg = kt % TSTG;
+        mbar_wait(&full_bar[stg], (kt / TSTG) & 1);
+        const double *As = smem + stg * TSTAGE_DOUBLES;
+        const double *Bs = As + TM * AS_LD;
+#pragma unroll
+        for (int k4 = 0; k4 < TK / 4; ++k4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = As[(wm * 32 + mi * 8 + g) * AS_LD + k4 * 4 + t4];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(k4 * 4 + t4) * BS_LD + wn * 32 + ni * 8 + g];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stg]);
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        const int r = rb + wm * 32 + mi * 8 + g;
+        if (r >= R.r1) continue;
+        double *row = M + (long long)r * ld;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
+            if (c0 < R.c1 && owned_col(ko, c0, F.f)) row[c0] = acc[mi][ni][0];
+            if (c0 + 1 < R.c1 && owned_col(ko, c0 + 1, F.f)) row[c0 + 1] = acc[mi][ni][1];
+        }
+    }
+}
+
+// =====================================================================================================
 // Large-region Schur update: CTA tile 128 x 128, 16 warps as 4 (M) x 4 (N), warp tile 32 x 32 = 4 x 4 DMMA tiles,
 // K staged 16 at a time through a 4-stage cp.async ring (global -> shared without touching registers), so loads
 // of stage t+3 overlap the DMMAs of stage t.  The accumulators start from the C tile itself (loaded while the
@@ -680,9 +818,12 @@ update_dmma_big_kernel(double *pool, long long pool_stride, const DFront *fronts
 
 int update_tile_m(int gemm_path) { return gemm_path == 1 ? FT : (gemm_path == 2 ? BM : TM); }
 int update_tile_n(int gemm_path) { return gemm_path == 1 ? FT : (gemm_path == 2 ? BN : TN); }
+int update_tile_k() { return TK; }
 
 void init_kernel_attributes() {
     cudaFuncSetAttribute(update_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)((size_t)TSTG * TSTAGE_DOUBLES * sizeof(double)));
+    cudaFuncSetAttribute(update_dmma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)((size_t)TSTG * TSTAGE_DOUBLES * sizeof(double)));
     cudaFuncSetAttribute(update_dmma_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)((size_t)STG * STAGE_DOUBLES * sizeof(double)));
@@ -696,6 +837,10 @@ void launch_update(const LaunchCtx &c, const int *ids, int nfb, int j, int mode,
     } else if (c.gemm_path == 2) {
         const size_t smem = (size_t)STG * STAGE_DOUBLES * sizeof(double);
         update_dmma_big_kernel<<<grid, 512, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split, c.ko);
+    } else if (c.gemm_path == 3) {
+        const size_t smem = (size_t)TSTG * TSTAGE_DOUBLES * sizeof(double);
+        update_dmma_tma_kernel<<<grid, TMA_THREADS, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split,
+                                                                     c.ko);
     } else {
         const size_t smem = (size_t)TSTG * TSTAGE_DOUBLES * sizeof(double);
         update_dmma_kernel<<<grid, 256, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split, c.ko);

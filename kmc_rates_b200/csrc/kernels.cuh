@@ -119,6 +119,7 @@ void init_kernel_attributes();
 // tile geometry used by the host to size grids
 int update_tile_m(int gemm_path);
 int update_tile_n(int gemm_path);
+int update_tile_k();
 
 // ---- ingest ---------------------------------------------------------------------------------------
 // sparse: CSR by source node; korig[e] = index of entry e in the caller's k array; dest[e] = pool offset
