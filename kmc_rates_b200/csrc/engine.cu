@@ -986,22 +986,17 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
     E->A.assign(A, A + nA);
     E->B.assign(B, B + nB);
     E->validate_groups();
-    std::vector<char> present(n, 0);
-    std::vector<int64_t> outdeg(n + 1, 0);
-    for (int64_t e = 0; e < nnz; ++e) {
-        if (src[e] < 0 || src[e] >= n || dst[e] < 0 || dst[e] >= n) throw InvalidError("rate endpoint out of range");
-        present[src[e]] = present[dst[e]] = 1;
-        outdeg[src[e] + 1]++;
-    }
+    ngt::EdgeIndex ix;
+    ngt::Adjacency g;
+    ngt::index_edges(n, nnz, src, dst, ix, g);
+    if (ix.range_error) throw InvalidError("rate endpoint out of range");
+    std::vector<char> &present = ix.present;
+    std::vector<int64_t> &outdeg = ix.outptr;     // row pointers of the CSR-by-source entry lists
     for (int64_t a : E->A) if (!present[a]) throw InvalidError("an element in the reactant set (A) is not in the graph");
     for (int64_t b : E->B) if (!present[b]) throw InvalidError("an element in the product set (B) is not in the graph");
     for (int64_t u = 0; u < n; ++u)
-        if (present[u] && outdeg[u + 1] == 0) throw InvalidError("node " + std::to_string(u) + " has no outgoing rate");
-
-    tm.lap("validate input");
-    ngt::Adjacency g;
-    ngt::build_adjacency(n, nnz, src, dst, g);
-    tm.lap("adjacency");
+        if (present[u] && outdeg[u + 1] == outdeg[u]) throw InvalidError("node " + std::to_string(u) + " has no outgoing rate");
+    tm.lap("index edges (validate, CSR buckets, adjacency)");
     // Nodes with no (undirected) path to A ∪ B cannot influence any result; like the reference's Python front end
     // (_kmc_rates.py:414-425) they are dropped before elimination.  Their committors read NaN.
     {
@@ -1025,10 +1020,7 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
     tm.lap("analyse_sparse total");
 
     // CSR by source over present nodes, (src,dst) duplicates resolved "last wins" (std::map semantics, ngt.pyx:76-81)
-    for (int64_t u = 0; u < n; ++u) outdeg[u + 1] += outdeg[u];
-    std::vector<int64_t> fill(outdeg.begin(), outdeg.end() - 1);
-    std::vector<int32_t> ent(nnz);
-    for (int64_t e = 0; e < nnz; ++e) ent[fill[src[e]]++] = (int32_t)e;   // stable: increasing e inside a row
+    const std::vector<int32_t> &ent = ix.ent;
     // rows = present nodes in id order; each worker thread handles a contiguous slice of rows twice:
     // pass 1 counts the entries that survive de-duplication, pass 2 writes source indices and slots.
     std::vector<int> row_node;

@@ -49,6 +49,101 @@ void build_adjacency(int64_t n, int64_t nnz, const int64_t *src, const int64_t *
 }
 
 namespace {
+template <class Fn>
+void parallel_ranges(int nthr, int64_t total, Fn &&fn) {
+    if (nthr <= 1) { fn(0, (int64_t)0, total); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthr; ++t) th.emplace_back([&, t] { fn(t, total * t / nthr, total * (t + 1) / nthr); });
+    for (auto &x : th) x.join();
+}
+}  // namespace
+
+void index_edges(int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, EdgeIndex &ix, Adjacency &g) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int T = (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
+    while (T > 1 && (double)T * n * 8.0 > 512e6) T /= 2;      // private counters: 8 bytes per node and thread
+    if (nnz < 200000) T = 1;
+    Timer tm;
+    std::vector<std::vector<int32_t> > c_out(T), c_adj(T);
+    std::vector<char> bad(T, 0);
+    ix.present.assign(n, 0);
+    // pass A: private counts per thread (each thread owns a contiguous slice of the entries)
+    parallel_ranges(T, nnz, [&](int t, int64_t e0, int64_t e1) {
+        c_out[t].assign(n, 0);
+        c_adj[t].assign(n, 0);
+        for (int64_t e = e0; e < e1; ++e) {
+            const int64_t u = src[e], v = dst[e];
+            if (u < 0 || u >= n || v < 0 || v >= n) { bad[t] = 1; continue; }
+            c_out[t][u]++;
+            if (u != v) { c_adj[t][u]++; c_adj[t][v]++; }
+            ix.present[u] = 1;     // benign race: every writer stores the same value
+            ix.present[v] = 1;
+        }
+    });
+    ix.range_error = false;
+    for (char b : bad) ix.range_error = ix.range_error || b;
+    if (ix.range_error) return;
+    tm.lap("  index: count");
+    // totals -> row pointers; private counts -> private write cursors
+    ix.outptr.assign(n + 1, 0);
+    std::vector<int64_t> aptr(n + 1, 0);
+    for (int64_t u = 0; u < n; ++u) {
+        int64_t so = 0, sa = 0;
+        for (int t = 0; t < T; ++t) { so += c_out[t][u]; sa += c_adj[t][u]; }
+        ix.outptr[u + 1] = ix.outptr[u] + so;
+        aptr[u + 1] = aptr[u] + sa;
+    }
+    std::vector<std::vector<int64_t> > w_out(T), w_adj(T);
+    for (int t = 0; t < T; ++t) { w_out[t].resize(n); w_adj[t].resize(n); }
+    parallel_ranges(T, n, [&](int /*tid*/, int64_t u0, int64_t u1) {
+        for (int64_t u = u0; u < u1; ++u) {
+            int64_t po = ix.outptr[u], pa = aptr[u];
+            for (int t = 0; t < T; ++t) {
+                w_out[t][u] = po; po += c_out[t][u];
+                w_adj[t][u] = pa; pa += c_adj[t][u];
+            }
+        }
+    });
+    tm.lap("  index: offsets");
+    // pass B: scatter
+    ix.ent.resize(nnz);
+    std::vector<int32_t> tmp(aptr[n]);
+    parallel_ranges(T, nnz, [&](int t, int64_t e0, int64_t e1) {
+        std::vector<int64_t> &wo = w_out[t], &wa = w_adj[t];
+        for (int64_t e = e0; e < e1; ++e) {
+            const int64_t u = src[e], v = dst[e];
+            ix.ent[wo[u]++] = (int32_t)e;
+            if (u != v) { tmp[wa[u]++] = (int32_t)v; tmp[wa[v]++] = (int32_t)u; }
+        }
+    });
+    tm.lap("  index: scatter");
+    // pass C: de-duplicate adjacency rows (marker per thread), then compact
+    std::vector<int64_t> ucnt(n + 1, 0);
+    parallel_ranges(T, n, [&](int /*t*/, int64_t u0, int64_t u1) {
+        std::vector<int32_t> seen(n, -1);
+        for (int64_t u = u0; u < u1; ++u) {
+            int64_t w = aptr[u];
+            for (int64_t q = aptr[u]; q < aptr[u + 1]; ++q) {
+                const int32_t v = tmp[q];
+                if (seen[v] == (int32_t)u) continue;
+                seen[v] = (int32_t)u;
+                tmp[w++] = v;          // in place inside the row
+            }
+            ucnt[u + 1] = w - aptr[u];
+        }
+    });
+    for (int64_t u = 0; u < n; ++u) ucnt[u + 1] += ucnt[u];
+    g.n = n;
+    g.ptr.assign(ucnt.begin(), ucnt.end());
+    g.adj.resize(ucnt[n]);
+    parallel_ranges(T, n, [&](int /*t*/, int64_t u0, int64_t u1) {
+        for (int64_t u = u0; u < u1; ++u)
+            std::copy(tmp.begin() + aptr[u], tmp.begin() + aptr[u] + (ucnt[u + 1] - ucnt[u]), g.adj.begin() + ucnt[u]);
+    });
+    tm.lap("  index: dedupe + compact");
+}
+
+namespace {
 
 // ---------------------------------------------------------------------------------------------
 // Nested dissection by BFS level structures (George's automatic nested dissection) on the graph

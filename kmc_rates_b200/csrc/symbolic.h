@@ -83,6 +83,16 @@ struct Adjacency {
 // Build the symmetrised adjacency of the rate graph.
 void build_adjacency(int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, Adjacency &g);
 
+// One parallel pass structure over the COO input (thread-private counting sort): range validation, presence flags,
+// CSR-by-source entry lists (stable: increasing entry index inside a row) and the symmetrised, de-duplicated adjacency.
+struct EdgeIndex {
+    std::vector<int64_t> outptr;   // n + 1
+    std::vector<int32_t> ent;      // nnz entry indices grouped by source node
+    std::vector<char> present;     // node appears in some rate
+    bool range_error = false;      // an endpoint was outside [0, n)
+};
+void index_edges(int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, EdgeIndex &ix, Adjacency &g);
+
 // Sparse network: nested dissection + supernodal symbolic factorisation.
 // present[u] = 0 marks ids that appear in no rate (they are ignored, like the reference which only
 // creates nodes named by a rate, ngt.hpp:114-117).
