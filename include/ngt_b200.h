@@ -41,7 +41,8 @@ typedef struct ngt_handle_s *ngt_handle;
 
 enum {
     NGT_OK = 0,
-    NGT_E_INVALID = 1,   /* bad argument: id out of range, A∩B≠∅, empty A or B, node without out-rates */
+    NGT_E_INVALID = 1,   /* bad argument: id out of range, A∩B≠∅, empty B, node without out-rates (A may be empty:
+                            MFPT-to-B mode, rates AB then read NaN) */
     NGT_E_CUDA = 2,      /* CUDA runtime error (no device, out of memory, launch failure) */
     NGT_E_STATE = 3,     /* call order: results requested before compute_* */
     NGT_E_NUMERIC = 4    /* a pivot 1-P_xx was zero or not finite (dead-end node) */

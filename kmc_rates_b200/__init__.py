@@ -10,5 +10,6 @@ library raises ImportError, and without a CUDA device RuntimeError.
 """
 from .graph_reduction import GraphReduction, kmcgraph_from_rates
 from .ngt import NGT, BaseNGT
+from .rates_linalg import TwoStateRates
 
-__all__ = ["GraphReduction", "kmcgraph_from_rates", "NGT", "BaseNGT"]
+__all__ = ["GraphReduction", "kmcgraph_from_rates", "NGT", "BaseNGT", "TwoStateRates"]

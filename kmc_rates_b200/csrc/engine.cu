@@ -304,7 +304,9 @@ struct Engine {
     }
 
     void validate_groups() {
-        if (A.empty() || B.empty()) throw InvalidError("A and B must each contain at least one node");
+        // A may be empty: then every node outside B is eliminated and the back-substitution yields the mean first
+        // passage time of every node into B (the linear-solve view, reference rates_linalg.py:246-285)
+        if (B.empty()) throw InvalidError("B must contain at least one node");
         std::vector<char> seen(n, 0);
         for (int64_t a : A) {
             if (a < 0 || a >= n) throw InvalidError("an element in the reactant set (A) is not in the graph");

@@ -125,3 +125,42 @@ def test_ngt_class_matches_reference_tests():
     assert abs(reducer.get_rate_AB_SS() - 19.933950145409426) < 1e-7
     assert abs(reducer.get_rate_BA_SS() - 6.970856553435547) < 1e-7
     assert reducer.time_solve > 0
+
+
+@pytest.mark.parametrize("A,B,weighted", [([0], [1], False), ([0, 1], [2, 3], False), ([0, 1], [2, 3], True), (list(range(8)), [9], False)])
+def test_two_state_rates_twin_matches_linear_solve(A, B, weighted):
+    """GPU twin of rates_linalg.TwoStateRates against the restated scipy version (reference tests/test_kmc.py:40-59,
+    tests/test_linalg.py:12-21)"""
+    from kmc_rates_b200 import TwoStateRates, synth
+    from oracle.py_linalg import TwoStateRatesCOO
+    rates = synth.random_connected_graph(10, 20, A + B, seed=11 + len(A))
+    rng = np.random.RandomState(3)
+    weights = {x: rng.uniform(0, 1) for x in A} if weighted else None
+    lin = TwoStateRates(rates, A, B, weights=weights)
+    lin.compute_rates()
+    lin.compute_committors()
+    nodes = sorted({u for uv in lin.rate_constants for u in uv})
+    idx = {u: i for i, u in enumerate(nodes)}
+    src = np.array([idx[u] for (u, v) in lin.rate_constants]); dst = np.array([idx[v] for (u, v) in lin.rate_constants])
+    k = np.array(list(lin.rate_constants.values()))
+    ref = TwoStateRatesCOO(len(nodes), src, dst, k, [idx[a] for a in A], [idx[b] for b in B],
+                           weights={idx[a]: w for a, w in weights.items()} if weights else None)
+    ref.compute_rates(); ref.compute_committors()
+    assert abs(lin.get_rate_AB() - ref.get_rate_AB()) < 1e-9 * ref.get_rate_AB()
+    assert abs(lin.get_rate_AB_SS() - ref.get_rate_AB_SS()) < 1e-9 * ref.get_rate_AB_SS()
+    for u, t in lin.mfptimes.items():
+        assert abs(t - ref.mfpt[idx[u]]) < 1e-9 * ref.mfpt[idx[u]]
+    for u, q in lin.committor_dict.items():
+        assert abs(q - ref.q[idx[u]]) < 1e-9
+    assert lin.get_committor(A[0]) == 0.0 and lin.get_committor(B[0]) == 1.0
+
+
+def test_two_state_rates_three_state():
+    """reference tests/test_linalg.py:6-28: k = 1.0, k_SS = 1.5"""
+    from kmc_rates_b200 import TwoStateRates
+    for i, j in ((0, 1), (1, 2), (0, 2)):
+        red = TwoStateRates(_three_state_rates(), [i], [j])
+        red.compute_rates()
+        assert abs(red.get_rate_AB() - 1.0) < 1e-7
+        red.compute_committors()
+        assert abs(red.get_rate_AB_SS() - 1.5) < 1e-7
