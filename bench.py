@@ -240,6 +240,49 @@ def dense_object(torch, Handle, dgemm_tflops, n=16384, steps=2):
     return out
 
 
+def other_configs_object(torch, Handle):
+    """the remaining BASELINE configs at 1 GPU, each a short measurement (details: DESIGN.md §5, profiles/)"""
+    from kmc_rates_b200 import GraphReduction, synth
+    out = {}
+    # config 1: README-style random complete graph, 100 nodes, through the drop-in GraphReduction API
+    rng = np.random.default_rng(0)
+    rates = {(i, j): float(rng.random()) for i in range(100) for j in range(100) if i != j}
+    GraphReduction(rates, [0], [1]).compute_rates()
+    t0 = time.perf_counter()
+    red = GraphReduction(rates, [0], [1])
+    red.compute_rates()
+    kab = red.get_rate_AB()
+    out["config1_complete100_GraphReduction_api"] = {"ms_end_to_end": 1e3 * (time.perf_counter() - t0), "k_AB": kab}
+    # config 4: 2*10^4-node landscape, |A| = |B| = 512 (phase 2 = 1024 independent per-a eliminations)
+    n, src, dst, k, A, B = synth.landscape_groups(141, 512, 512, T=TEMPERATURE, seed=0)
+    h = Handle.from_coo(n, src, dst, k, A, B)
+    h.compute_rates()
+    h.phase_one(); h.phase_two()
+    st = h.stats()
+    out["config4_19881_nodes_A512_B512"] = {"phase1_ms": st["ms_phase1"], "phase2_ms": st["ms_phase2"],
+                                            "per_a_reductions_per_s": 1024 / (st["ms_phase2"] * 1e-3),
+                                            "k_AB": float(h.rates()[0]), "k_BA": float(h.rates()[1])}
+    h.close()
+    # config 5: 4096 independent 256-node networks (temperature sweep), one batched handle
+    NB, N = 4096, 256
+    gen = torch.Generator(device="cuda"); gen.manual_seed(0)
+    E = torch.rand(N, generator=gen, dtype=torch.float64, device="cuda")
+    bar = torch.rand(N, N, generator=gen, dtype=torch.float64, device="cuda") * 0.9 + 0.1
+    bar = torch.maximum(bar, bar.T)
+    temps = torch.logspace(np.log10(0.05), 0.0, NB, dtype=torch.float64, device="cuda")
+    K = torch.exp(-((torch.maximum(E[:, None], E[None, :]) + bar)[None] - E[None, :, None]) / temps[:, None, None])
+    K.diagonal(dim1=1, dim2=2).zero_()
+    h = Handle.from_dense(K, [0], [N - 1])
+    h.timed_steps(1)
+    ms = h.timed_steps(3) / 3
+    out["config5_4096x256_sweep"] = {"ms_per_sweep": ms, "networks_per_s": NB / (ms * 1e-3),
+                                     "nodes_eliminated_per_s": NB * (N - 2) / (ms * 1e-3)}
+    h.close()
+    del K
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -384,6 +427,12 @@ def main():
                 dense = dense_object(torch, Handle, dgemm, n=args.dense_n)
             except Exception as e:   # report, do not hide
                 dense = {"error": repr(e)}
+        other = None
+        if world == 1 and not args.no_dense:
+            try:
+                other = other_configs_object(torch, Handle)
+            except Exception as e:
+                other = {"error": repr(e)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -398,6 +447,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "dense": dense,
+            "other_configs": other,
             "stats": {"nodes_eliminated_per_step": nodes_per_step, "rates": nnz, "fronts": st["n_fronts"],
                       "levels": st["n_levels"], "max_front": st["max_front"], "pool_GB": st["pool_doubles"] * 8 / 1e9,
                       "alg_flops": st["alg_flops"], "ms_symbolic_host": st["ms_symbolic"], "ms_ingest": st["ms_ingest"],
