@@ -793,6 +793,8 @@ struct Engine {
     static constexpr int LD_PAN = ngt::NB_OUTER + 8;
     static constexpr int W_DOUBLES = (ngt::NB_OUTER / ngt::NB_INNER) * ngt::NB_INNER * ngt::NB_INNER;
     DevBuf<double> d_pan, d_spart, d_tauglob, d_rootc;
+    size_t pan_stride = 0;
+    double *pan_buf(int J) { return d_pan.p + (size_t)((J / ngt::NB_OUTER) & 1) * pan_stride; }
     DevBuf<DFront> d_dfronts;   // [0] panel front, [1] big matrix with the panel as A operand
     DevBuf<int> d_dids;
 
@@ -807,12 +809,14 @@ struct Engine {
         dist_G = G;
         dist_g = g;
         const ngt::Front &F0 = S.fronts[0];
-        d_pan.alloc((size_t)W_DOUBLES + (size_t)F0.f * LD_PAN);
+        pan_stride = (size_t)W_DOUBLES + (size_t)F0.f * LD_PAN;
+        d_pan.alloc(2 * pan_stride);   // double buffered: block J+1's panel arrives while block J's update still reads J's
         d_spart.alloc(ngt::NB_OUTER);
         d_tauglob.alloc((size_t)n);
         d_rootc.alloc((size_t)m * m);
-        d_dfronts.alloc(2);
-        d_dids.upload(std::vector<int>{0, 1});
+        d_dfronts.alloc(3);            // [0] panel front, [1]/[2] big matrix with panel buffer 0/1 as A operand
+        d_dids.upload(std::vector<int>{0, 1, 2});
+        d2_pending = false;
         maxfb = std::max(maxfb, ngt::NB_OUTER / ngt::NB_INNER);
         d_wbuf.alloc((size_t)nbatch * maxfb * ngt::NB_INNER * ngt::NB_INNER);
         st.n_launches = 0;
@@ -846,7 +850,7 @@ struct Engine {
         dist_check(J);
         const ngt::Front &F0 = S.fronts[0];
         const int JE = block_end(J), kb = JE - J, fr = F0.f - J;
-        double *pan = d_pan.p + W_DOUBLES;
+        double *pan = pan_buf(J) + W_DOUBLES;
         ngt::launch_dist_pack(d_pool.p + F0.off, F0.ld, J, kb, fr, pan, LD_PAN, d_spart.p, d_tauglob.p, stream);
         DFront P{};
         P.off = pan - d_pool.p;          // the kernels address fronts relative to the pool base
@@ -871,36 +875,40 @@ struct Engine {
         }
         wslot_per_step = false;
         use_lookahead = la;
-        CK(cudaMemcpyAsync(d_pan.p, d_wbuf.p, W_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        CK(cudaMemcpyAsync(pan_buf(J), d_wbuf.p, W_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice, stream));
         CK(cudaStreamSynchronize(stream));
     }
 
     // what travels: [W of the block's inner panels | panel front rows J..f-1]
     void dist_panel(int J, double **ptr, int64_t *cnt) {
         dist_check(J);
-        *ptr = d_pan.p;
+        *ptr = pan_buf(J);
         *cnt = (int64_t)W_DOUBLES + (int64_t)(S.fronts[0].f - J) * LD_PAN;
     }
 
-    // everybody: replay the block's row operations on the own columns, then the trailing update with the panel as A
+    // everybody: replay the block's row operations on the own columns, then the trailing update with the panel as A.
+    // Look-ahead: only the strips the NEXT block needs (its columns, its rows) are updated on the main stream; the
+    // rest of the trailing update runs on the second stream and overlaps the next block's row sums, all-reduce,
+    // panel factorisation and broadcast.  The call returns when the main stream is done.
     void dist_apply(int J) {
         dist_check(J);
         const ngt::Front &F0 = S.fronts[0];
         const int JE = block_end(J), kb = JE - J, fr = F0.f - J;
-        const double *pan = d_pan.p + W_DOUBLES;
-        CK(cudaMemcpyAsync(d_wbuf.p, d_pan.p, W_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        const int par = (J / ngt::NB_OUTER) & 1;
+        const double *pan = pan_buf(J) + W_DOUBLES;
+        CK(cudaMemcpyAsync(d_wbuf.p, pan_buf(J), W_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice, stream));
         ngt::launch_dist_tau(pan, LD_PAN, kb, fr, J, d_tauglob.p, stream);
         DFront B{};
         B.off = F0.off; B.f = F0.f; B.k = F0.k; B.ld = F0.ld; B.parent = -1; B.fr = 0;
         B.a_ld = LD_PAN;
         B.a_off = (pan - d_pool.p) - (long long)J * LD_PAN - J;   // A(r, p) = pan[(r - J) * LD_PAN + (p - J)]
-        CK(cudaMemcpyAsync(d_dfronts.p + 1, &B, sizeof(DFront), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_dfronts.p + 1 + par, &B, sizeof(DFront), cudaMemcpyHostToDevice, stream));
         HostBatch hb;
-        hb.ids = {1}; hb.f = {B.f}; hb.k = {B.k}; hb.max_k = B.k; hb.dev_off = 0;
+        hb.ids = {1 + par}; hb.f = {B.f}; hb.k = {B.k}; hb.max_k = B.k; hb.dev_off = 0;
         const int tm = ngt::update_tile_m(opt.gemm_path), tn = ngt::update_tile_n(opt.gemm_path);
         ngt::LaunchCtx c = ctx(d_pool.p, pool_stride, d_dfronts.p);
         c.ko = own();
-        const int *ids = d_dids.p + 1;
+        const int *ids = d_dids.p + 1 + par;
         double fl = 0;
         for (int j = J; j < JE; j += ngt::NB_INNER) {
             c.ko.wslot = (j - J) / ngt::NB_INNER;
@@ -911,9 +919,26 @@ struct Engine {
             st.n_launches += 2;
         }
         const int jl = J + ((kb - 1) / ngt::NB_INNER) * ngt::NB_INNER;
-        const int td = max_tiles(hb, jl, ngt::MODE_D, tm, tn, fl);
-        if (td > 0) ngt::launch_update(c, ids, 1, jl, ngt::MODE_D, td, 0);
-        st.n_launches++;
+        const int t1a = max_tiles(hb, jl, ngt::MODE_D1A, tm, tn, fl);
+        const int t1b = max_tiles(hb, jl, ngt::MODE_D1B, tm, tn, fl);
+        const int t2 = max_tiles(hb, jl, ngt::MODE_D2, tm, tn, fl);
+        // the strips (and everything after them) touch the region the previous block's D2 was writing
+        if (d2_pending) { CK(cudaStreamWaitEvent(stream, sync_event(1), 0)); d2_pending = false; }
+        if (t1a + t1b > 0) { ngt::launch_update(c, ids, 1, jl, ngt::MODE_D1, t1a + t1b, t1a); st.n_launches++; }
+        if (t2 > 0) {
+            if (use_lookahead) {
+                CK(cudaEventRecord(sync_event(0), stream));
+                CK(cudaStreamWaitEvent(stream2, sync_event(0), 0));
+                ngt::LaunchCtx c2 = c;
+                c2.stream = stream2;
+                ngt::launch_update(c2, ids, 1, jl, ngt::MODE_D2, t2, 0);
+                CK(cudaEventRecord(sync_event(1), stream2));
+                d2_pending = true;
+            } else {
+                ngt::launch_update(c, ids, 1, jl, ngt::MODE_D2, t2, 0);
+            }
+            st.n_launches++;
+        }
         st.schur_flops += fl / dist_G;   // region flops; a rank performs its 1/G share of the columns
         CK(cudaStreamSynchronize(stream));
     }
@@ -921,6 +946,7 @@ struct Engine {
     double *dist_root_contrib() {
         if (dist_G < 1) throw StateError("ngt_dist_begin has not been called");
         const ngt::Front &F0 = S.fronts[0];
+        if (d2_pending) { CK(cudaStreamWaitEvent(stream, sync_event(1), 0)); d2_pending = false; }
         ngt::launch_dist_root_contrib(d_pool.p + F0.off, F0.ld, F0.f, (int)S.nI, m, own(), d_rootc.p, stream);
         CK(cudaStreamSynchronize(stream));
         return d_rootc.p;

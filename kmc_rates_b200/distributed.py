@@ -97,26 +97,30 @@ def dense_phase_one_distributed(handle, group=None):
     """Phase 1 of one complete network spread over the ranks of `group` (every rank holds a handle created from the
     same rate matrix).  Per outer block: all-reduce of the block rows' outside mass (for the subtraction-free
     pivots), panel factorisation on the owning rank, NCCL broadcast of the factored panel, trailing update of the
-    own columns on every rank.  Afterwards handle.phase_two() / rates() work as usual on every rank."""
+    own columns on every rank.  Afterwards handle.phase_two() / rates() work as usual on every rank.
+
+    The engine runs the bulk of each trailing update on its own second stream while the next block's collectives
+    and panel proceed, so only the stream the collectives were issued on is synchronised here — never the device."""
     import torch
     dist = _dist()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    cur = torch.cuda.current_stream()
     handle.dist_begin(rank, world)
     npiv, block = handle.dist_info()
     for J in range(0, npiv, block):
         p, n = handle.dist_rowsum(J)
         dist.all_reduce(_dev_tensor(p, n), op=dist.ReduceOp.SUM, group=group)
-        torch.cuda.synchronize()      # the engine works on its own streams: the collective must have landed
+        cur.synchronize()             # the engine works on its own streams: the collective must have landed
         owner = (J // block) % world
         if rank == owner:
             handle.dist_factor(J)
         p, n = handle.dist_panel(J)
         dist.broadcast(_dev_tensor(p, n), src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
-        torch.cuda.synchronize()
+        cur.synchronize()
         handle.dist_apply(J)
     p, n = handle.dist_root()
     dist.all_reduce(_dev_tensor(p, n), op=dist.ReduceOp.SUM, group=group)
-    torch.cuda.synchronize()
+    cur.synchronize()
     handle.dist_finish()
 
 
