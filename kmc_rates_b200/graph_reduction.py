@@ -17,19 +17,11 @@ from .ngt import _label_maps, rates_to_coo
 
 
 def kmcgraph_from_rates(rates):
-    """create a graph for input to GraphReduction from a dictionary of rates
+    """Build the kinetic graph of a rate dictionary {(u, v): k_uv}.
 
-    Parameters
-    ----------
-    rates : dict
-        a dictionary of rates.  the keys are tuples of nodes (u,v), the values
-        are the rate constants from u to v.
-
-    Returns
-    -------
-    graph : networkx.DiGraph with node attribute "tau" (occupation time) and edge attribute "P"
-        (transition probability), including a self loop u->u with P=0 for every node
-        (reference _kmc_rates.py:18-66).
+    Returns a networkx.DiGraph whose nodes carry "tau" = 1 / sum_v k_uv (mean waiting time) and whose edges carry
+    "P" = k_uv * tau_u (branching probability); every node also gets a self loop with P = 0, the slot the
+    transformation later fills (same construction as reference _kmc_rates.py:18-66).
     """
     graph = nx.DiGraph()
     sumk = defaultdict(float)
@@ -55,25 +47,16 @@ def _rates_from_graph(graph):
 
 
 class GraphReduction(object):
-    """
-    class to apply the graph reduction method for finding transition rates between two groups of nodes
+    """Drop-in for the reference's GraphReduction (reference _kmc_rates.py:70-116) with the arithmetic on B200.
 
-    Parameters
-    ----------
-    rate_constants : dict (or a graph made by kmcgraph_from_rates)
-        a dictionary of rates.  the keys are tuples of nodes (u,v), the values
-        are the rate constants from u to v.
-    A, B : iterables
-        Groups of nodes specifying the reactant and product groups.  The rates
-        returned will be the rate from A to B and vice versa.
-    weights : dict
-        Dictionary with nodes as keys and weights as values.  The weights are
-        the equilibrium occupation probabilities of the nodes in A and B.
+    rate_constants : dict {(u, v): k_uv}, or a graph made by kmcgraph_from_rates
+    A, B           : reactant and product groups (iterables of node labels)
+    weights        : optional dict node -> equilibrium occupation probability for the final weighted averages
+    debug          : accepted for compatibility
 
-    Notes
-    -----
-    New graph transformation (NGT), David Wales, J. Chem. Phys., 2009 http://dx.doi.org/10.1063/1.3133782.
-    The rate k_AB is the inverse mean first passage time averaged over the states in A.
+    After compute_rates(): get_rate_AB(), get_rate_BA(), get_rate_AB_SS(), get_committor_probabilityAB(x);
+    compute_committor_probabilities(nodes) works before or after.  `graph` is the full kinetic graph before
+    compute_rates() and the graph reduced to A ∪ B afterwards, as in the reference.
     """
 
     def __init__(self, rate_constants, A, B, debug=False, weights=None, device=0, gemm_path=0, leaf_size=0):

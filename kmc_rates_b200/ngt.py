@@ -34,24 +34,18 @@ def rates_to_coo(rate_constants, node2id):
 
 
 class BaseNGT(object):
-    """
-    class to apply the graph reduction method for finding transition rates between two groups of nodes
+    """Transition rates between two groups of nodes by graph transformation, computed on the GPU.
 
-    Parameters
-    ----------
-    rate_constants : dict
-        a dictionary of rates.  the keys are tuples of nodes (u,v), the values
-        are the rate constants from u to v.
-    A, B : iterables
-        Groups of nodes specifying the reactant and product groups.  The rates
-        returned will be the rate from A to B and vice versa.
-    weights : dict
-        Dictionary with nodes as keys and weights as values.  The weights are
-        the equilibrium occupation probabilities of the nodes in A and B.  They
-        are used to do the weighted mean for the final average over inverse
-        mean first passage times.
+    rate_constants : dict mapping (u, v) -> rate constant of the move u -> v (any hashable node labels)
+    A, B           : the reactant and the product group; the results are k_AB and k_BA
+    weights        : optional dict node -> equilibrium occupation probability, used to weight the average of
+                     inverse mean first-passage times over the members of A (and of B)
+    debug          : accepted for compatibility with the reference signature
     device, gemm_path, leaf_size : B200-side options (CUDA ordinal; 0 = DMMA tensor cores, 1 = scalar DFMA
-        cross-check path; nested-dissection leaf size)
+                     cross-check path; nested-dissection leaf size)
+
+    k_AB is the inverse mean first-passage time from a to B averaged over a in A (Wales, J. Chem. Phys. 130,
+    204111 (2009)); constructor and methods mirror reference kmc_rates/ngt.pyx:31-154.
     """
     time_solve = 0.
 
@@ -111,10 +105,10 @@ class BaseNGT(object):
         self.time_solve = time.perf_counter() - t0
 
     def compute_rates_and_committors(self):
-        """compute the rates from A->B and B->A and the committors for all the intermediates
+        """rates in both directions plus the committor of every intermediate node
 
-        The reference warns this is "much slower than compute_rates" (it re-runs a full elimination per
-        intermediate, ngt.hpp:553-608); here it is one back-substitution over the kept factors.
+        The reference re-runs a full elimination per intermediate (ngt.hpp:553-608, "much slower"); here it is one
+        back-substitution over the factors phase 1 leaves behind.
         """
         t0 = time.perf_counter()
         self._h.compute_rates_and_committors()
