@@ -11,6 +11,8 @@
 #include "kernels.cuh"
 #include "symbolic.h"
 
+#include <cuda.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -213,6 +215,37 @@ struct Engine {
 
     bool use_big_kernel = std::getenv("NGT_B200_BIG") != nullptr;   // 128 x 128 kernel: measured slower than 2 CTAs/SM of 128 x 64
     bool use_lookahead = std::getenv("NGT_B200_NO_LOOKAHEAD") == nullptr;
+    // 2-D tensor maps over the single front of a dense handle (A box 16 x 128, B box 16 x 16, 128-byte swizzle)
+    CUtensorMap tmapA{}, tmapB{};
+    bool have_tmaps = false;
+    bool use_tmap = std::getenv("NGT_B200_NO_TMAP") == nullptr;
+    void make_tensor_maps() {
+        have_tmaps = false;
+        if (!dense || nbatch != 1 || S.nI <= 0) return;
+        typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+            qres != cudaDriverEntryPointSuccess)
+            return;
+        const ngt::Front &F0 = S.fronts[0];
+        void *base = d_pool.p + F0.off;
+        const cuuint64_t gdim[2] = {(cuuint64_t)F0.ld, (cuuint64_t)F0.f};
+        const cuuint64_t gstride[1] = {(cuuint64_t)F0.ld * sizeof(double)};
+        const cuuint32_t estr[2] = {1, 1};
+        const cuuint32_t boxA[2] = {16, 128}, boxB[2] = {16, 16};
+        EncodeFn enc = reinterpret_cast<EncodeFn>(fn);
+        const CUresult ra = enc(&tmapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, boxA, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        const CUresult rb = enc(&tmapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, boxB, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        have_tmaps = (ra == CUDA_SUCCESS && rb == CUDA_SUCCESS);
+    }
+
     // Bulk-copy (TMA, cp.async.bulk + mbarrier) fed variant of the Schur kernel: correct, but with one 128-byte bulk
     // copy per tile row it measured 3x SLOWER than the cp.async ring (dense 16 384: 343 ms vs 117 ms per step) — the
     // copy engine wants KB-sized boxes.  Opt-in (NGT_B200_TMA=1) until the 2-D tensor-map version replaces it.
@@ -558,14 +591,22 @@ struct Engine {
                     timed(stream, [&] { ngt::launch_update(cj, ids, nfb, j, ngt::MODE_D1, td1a + td1b, td1a); });
                 }
                 if (td2 > 0) {
+                    const bool via_tmap = use_tmap && have_tmaps && opt.gemm_path == 0 && c2.gemm_path == 0 && nfb == 1 &&
+                                          c.fronts == d_fronts.p && b.ids[0] == 0 && tma_eligible(b, 0, j, ngt::MODE_D2);
                     if (d2_async) {
                         c2.stream = stream2;
-                        timed(stream2, [&] { ngt::launch_update(c2, ids, nfb, j, ngt::MODE_D2, td2, 0); });
+                        timed(stream2, [&] {
+                            if (via_tmap) ngt::launch_update_tmap(c2, ids, j, ngt::MODE_D2, td2, &tmapA, &tmapB);
+                            else ngt::launch_update(c2, ids, nfb, j, ngt::MODE_D2, td2, 0);
+                        });
                         CK(cudaEventRecord(sync_event(1), stream2));
                         d2_pending = true;
                     } else {
                         if (d2_pending) { CK(cudaStreamWaitEvent(stream, sync_event(1), 0)); d2_pending = false; }
-                        timed(stream, [&] { ngt::launch_update(c2, ids, nfb, j, ngt::MODE_D2, td2, 0); });
+                        timed(stream, [&] {
+                            if (via_tmap) ngt::launch_update_tmap(c2, ids, j, ngt::MODE_D2, td2, &tmapA, &tmapB);
+                            else ngt::launch_update(c2, ids, nfb, j, ngt::MODE_D2, td2, 0);
+                        });
                     }
                 }
             }
@@ -1150,6 +1191,7 @@ void build_dense(Engine *E, int64_t n, const double *K, bool on_device, int64_t 
     E->init_device();
     E->d_pos.upload(E->S.pos);
     E->upload_structure();
+    E->make_tensor_maps();
     if (K) {
         if (on_device) {
             E->d_K = K;

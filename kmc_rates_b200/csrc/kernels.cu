@@ -2,6 +2,8 @@
 // Layout and the blocked elimination scheme are described in kernels.cuh.
 #include "kernels.cuh"
 
+#include <cuda.h>
+
 #include <cstdio>
 
 namespace ngt {
@@ -699,6 +701,141 @@ update_dmma_tma_kernel(double *pool, long long pool_stride, const DFront *fronts
 }
 
 // =====================================================================================================
+// Schur update fed by 2-D tensor-map TMA (`cp.async.bulk.tensor.2d` -> SASS UTMALDG) for large single-front
+// trailing updates.  Per 16-pivot stage the producer warp issues FIVE copies: one 16 x 128 box of A (16 KB) and four
+// 16 x 16 boxes of B (2 KB each; a 128-byte-swizzled box may not be wider than 128 bytes), all landing on the stage's
+// "full" mbarrier; 4 stages (96 KB) x 2 CTAs per SM.  Tiles sit densely in shared memory with the hardware
+// 128-byte swizzle (16-byte chunk c of row r is stored at chunk c ^ (r & 7)), which makes the A fragment loads
+// conflict free and the B fragment loads 2-way (4 wavefronts instead of 2).  The math warps only wait, LDS and DMMA.
+// Tile geometry and accumulation order equal update_dmma_kernel, so results are bitwise identical.
+// =====================================================================================================
+constexpr int TMS = 4;                                  // stages
+constexpr int TM_A_DOUBLES = TM * TK;                   // 128 x 16
+constexpr int TM_B_DOUBLES = TK * TN;                   // 16 x 64 as four 16 x 16 sub-tiles
+constexpr int TM_STAGE_DOUBLES = TM_A_DOUBLES + TM_B_DOUBLES;
+constexpr unsigned TM_STAGE_BYTES = TM_STAGE_DOUBLES * 8;
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, int y, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2)
+update_dmma_tmap_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode_in,
+                        int split, KOpt ko, const __grid_constant__ CUtensorMap tmA,
+                        const __grid_constant__ CUtensorMap tmB) {
+    const DFront F = fronts[ids[blockIdx.y]];
+    Region R;
+    int mode = mode_in, tile = blockIdx.x;
+    if (mode_in == MODE_AB) {
+        if (tile < split) mode = MODE_A; else { mode = MODE_B; tile -= split; }
+    } else if (mode_in == MODE_D1) {
+        if (tile < split) mode = MODE_D1A; else { mode = MODE_D1B; tile -= split; }
+    }
+    if (!get_region(F.f, F.fr, F.k, j, mode, R)) return;
+    const int tiles_c = (R.c1 - R.c0 + TN - 1) / TN;
+    const int tiles_r = (R.r1 - R.r0 + TM - 1) / TM;
+    const int tr = tile / tiles_c, tc = tile % tiles_c;
+    if (tr >= tiles_r) return;
+    double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
+    const int rb = R.r0 + tr * TM, cb = R.c0 + tc * TN;
+    const long long ld = F.ld;
+
+    extern __shared__ __align__(1024) double smem[];
+    __shared__ unsigned long long full_bar[TMS], empty_bar[TMS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < TMS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nk = (R.k1 - R.k0) / TK;                      // host guarantees K % 16 == 0
+
+    // the copy engine is driven by one elected thread of warp 0, which is also a math warp: issuing a stage is five
+    // instructions, so a dedicated producer warp would only cost registers and occupancy (2 CTAs/SM need <= 8 warps)
+    auto issue_stage = [&](int kt) {
+        const int stg = kt % TMS;
+        if (kt >= TMS) mbar_wait(&empty_bar[stg], ((kt / TMS) - 1) & 1);   // all 8 warps are done with its last use
+        const int kb = R.k0 + kt * TK;
+        double *As = smem + stg * TM_STAGE_DOUBLES;
+        double *Bs = As + TM_A_DOUBLES;
+        mbar_expect_tx(&full_bar[stg], TM_STAGE_BYTES);
+        tma_load_2d(As, &tmA, kb, rb, &full_bar[stg]);                      // A[rb.., kb..kb+16)
+#pragma unroll
+        for (int sb = 0; sb < TN / 16; ++sb)                                 // B[kb..kb+16, cb+16 sb ..)
+            tma_load_2d(Bs + sb * 256, &tmB, cb + 16 * sb, kb, &full_bar[stg]);
+    };
+    if (threadIdx.x == 0)
+        for (int kt = 0; kt < TMS - 1 && kt < nk; ++kt) issue_stage(kt);
+
+    const int wm = warp & 3, wn = warp >> 2;
+    const int g = lane >> 2, t4 = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        const int r = rb + wm * 32 + mi * 8 + g;
+        const double *row = M + (long long)r * ld;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
+            acc[mi][ni][0] = (r < R.r1 && c0 < R.c1) ? row[c0] : 0.0;
+            acc[mi][ni][1] = (r < R.r1 && c0 + 1 < R.c1) ? row[c0 + 1] : 0.0;
+        }
+    }
+    // swizzled fragment addresses: a lane-constant base plus compile-time offsets.
+    //   A[m][k]: m = wm*32 + mi*8 + g, k = 4 k4 + t4 -> doubles m*16 + 2*((k>>1) ^ g) + (k&1); (k>>1) ^ g = (g ^ (t4>>1)) ^ 2 k4
+    //   B[k][n]: n = wn*32 + ni*8 + g -> sub-tile n>>4, column c = (ni&1)*8 + g -> doubles
+    //            (n>>4)*256 + k*16 + 2*((c>>1) ^ (k&7)) + (c&1);  (c>>1) ^ (k&7) = 4*((ni ^ k4) & 1) + ((g>>1) ^ t4)
+    const int a_base = (wm * 32 + g) * 16 + (t4 & 1);
+    const int ga = g ^ (t4 >> 1);
+    const int b_base = wn * 512 + t4 * 16 + ((((g >> 1) ^ t4) << 1) | (g & 1));
+    for (int kt = 0; kt < nk; ++kt) {
+        const int stg = kt % TMS;
+        if (threadIdx.x == 0 && kt + TMS - 1 < nk) issue_stage(kt + TMS - 1);
+        mbar_wait(&full_bar[stg], (kt / TMS) & 1);
+        const double *As = smem + stg * TM_STAGE_DOUBLES;
+        const double *Bs = As + TM_A_DOUBLES;
+#pragma unroll
+        for (int k4 = 0; k4 < TK / 4; ++k4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = As[a_base + mi * 128 + ((ga ^ (2 * k4)) << 1)];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[b_base + (ni >> 1) * 256 + k4 * 64 + (((ni ^ k4) & 1) << 3)];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stg]);
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        const int r = rb + wm * 32 + mi * 8 + g;
+        if (r >= R.r1) continue;
+        double *row = M + (long long)r * ld;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
+            if (c0 < R.c1 && owned_col(ko, c0, F.f)) row[c0] = acc[mi][ni][0];
+            if (c0 + 1 < R.c1 && owned_col(ko, c0 + 1, F.f)) row[c0 + 1] = acc[mi][ni][1];
+        }
+    }
+}
+
+void launch_update_tmap(const LaunchCtx &c, const int *ids, int j, int mode, int max_tiles, const void *tmA,
+                        const void *tmB) {
+    if (max_tiles <= 0) return;
+    dim3 grid(max_tiles, 1, c.nbatch);
+    const size_t smem = (size_t)TMS * TM_STAGE_BYTES;
+    update_dmma_tmap_kernel<<<grid, 256, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, 0, c.ko,
+                                                                  *static_cast<const CUtensorMap *>(tmA),
+                                                                  *static_cast<const CUtensorMap *>(tmB));
+}
+
+// =====================================================================================================
 // Large-region Schur update: CTA tile 128 x 128, 16 warps as 4 (M) x 4 (N), warp tile 32 x 32 = 4 x 4 DMMA tiles,
 // K staged 16 at a time through a 4-stage cp.async ring (global -> shared without touching registers), so loads
 // of stage t+3 overlap the DMMAs of stage t.  The accumulators start from the C tile itself (loaded while the
@@ -825,6 +962,11 @@ void init_kernel_attributes() {
                          (int)((size_t)TSTG * TSTAGE_DOUBLES * sizeof(double)));
     cudaFuncSetAttribute(update_dmma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)((size_t)TSTG * TSTAGE_DOUBLES * sizeof(double)));
+    cudaFuncSetAttribute(update_dmma_tmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)((size_t)TMS * TM_STAGE_BYTES));
+    cudaFuncSetAttribute(update_dmma_tmap_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         (int)cudaSharedmemCarveoutMaxShared);   // two 97 KB CTAs per SM
+
     cudaFuncSetAttribute(update_dmma_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)((size_t)STG * STAGE_DOUBLES * sizeof(double)));
 }

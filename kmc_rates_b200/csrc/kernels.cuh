@@ -113,6 +113,11 @@ void launch_rowpanel(const LaunchCtx &c, const int *ids, int nfb, int j, int max
 // mode MODE_AB runs both L-shaped regions in one launch: CTAs [0, split) do MODE_A, the rest MODE_B
 void launch_update(const LaunchCtx &c, const int *ids, int nfb, int j, int mode, int max_tiles, int split);
 
+// tensor-map (TMA) fed Schur update of ONE front: tmA / tmB point to CUtensorMap objects over the front's matrix with
+// boxes of 16 x 128 and 16 x 16 doubles (128-byte swizzle); see Engine::make_tensor_maps
+void launch_update_tmap(const LaunchCtx &c, const int *ids, int j, int mode, int max_tiles, const void *tmA,
+                        const void *tmB);
+
 // opt-in shared-memory sizes of the DMMA kernels (call once per process/device before the first launch)
 void init_kernel_attributes();
 
