@@ -551,16 +551,31 @@ void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
     std::vector<std::vector<int32_t> > upd(ns);   // update sets (freed into fidx at the end)
     for (int32_t s = 0; s < ns; ++s)
         for (int32_t p = sn_start[s]; p < sn_start[s + 1]; ++p) S.pos_front[p] = s;
+    // phase A (parallel over supernodes): the later neighbours of each supernode's own pivots, sorted and unique
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        int T = (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
+        if (ns < 256) T = 1;
+        parallel_ranges(T, ns, [&](int /*t*/, int64_t s0, int64_t s1) {
+            std::vector<int32_t> mk(npos, -1);
+            for (int64_t s = s0; s < s1; ++s) {
+                const int32_t first = sn_start[s], last = sn_start[s + 1];
+                std::vector<int32_t> &U = upd[s];
+                for (int32_t p = first; p < last; ++p) {
+                    const int32_t u = S.node_at[p];
+                    for (int64_t e = g.ptr[u]; e < g.ptr[u + 1]; ++e) {
+                        const int32_t q = S.pos[g.adj[e]];
+                        if (q >= last && mk[q] != (int32_t)s) { mk[q] = (int32_t)s; U.push_back(q); }
+                    }
+                }
+            }
+        });
+    }
+    // phase B (in elimination order): add what the children pass up
     for (int32_t s = 0; s < ns; ++s) {
         const int32_t first = sn_start[s], last = sn_start[s + 1];
         std::vector<int32_t> &U = upd[s];
-        for (int32_t p = first; p < last; ++p) {
-            const int32_t u = S.node_at[p];
-            for (int64_t e = g.ptr[u]; e < g.ptr[u + 1]; ++e) {
-                const int32_t q = S.pos[g.adj[e]];
-                if (q >= last && mark[q] != s) { mark[q] = s; U.push_back(q); }
-            }
-        }
+        for (int32_t q : U) mark[q] = s;
         for (int32_t c : kids[s])
             for (int32_t q : upd[c])
                 if (q >= last && mark[q] != s) { mark[q] = s; U.push_back(q); }
