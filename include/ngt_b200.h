@@ -53,9 +53,7 @@ typedef struct ngt_options {
     int32_t device;          /* CUDA device ordinal */
     int32_t gemm_path;       /* 0 = FP64 tensor-core DMMA, tile chosen per launch (default); 1 = scalar DFMA (cross-check); 2 = DMMA 128x128 cp.async kernel everywhere */
     int32_t leaf_size;       /* nested-dissection leaf size (0 -> 64) */
-    int32_t keep_factor;     /* 1 = keep eliminated rows for committor back-substitution */
-    int32_t phase2_closed_form; /* 1 = also evaluate phase 2 by the closed form 1/G_aa as a cross-check */
-    int32_t reserved[11];
+    int32_t reserved[13];    /* must be zero */
 } ngt_options;
 
 /* ---- construction ------------------------------------------------------------------------- */

@@ -24,9 +24,7 @@ class Options(ctypes.Structure):
         ("device", ctypes.c_int32),
         ("gemm_path", ctypes.c_int32),
         ("leaf_size", ctypes.c_int32),
-        ("keep_factor", ctypes.c_int32),
-        ("phase2_closed_form", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 11),
+        ("reserved", ctypes.c_int32 * 13),
     ]
 
 

@@ -171,13 +171,13 @@ struct Engine {
     // device: structure
     DevBuf<DFront> d_fronts;
     DevBuf<int> d_ids;              // batch ids (phase 1), then extend-add rounds
-    DevBuf<int> d_rel;
-    DevBuf<long long> d_rel_off;
+    DevBuf<int> d_inv, d_child_ids;
+    DevBuf<long long> d_inv_off, d_child_ptr;
     DevBuf<int> d_fidx;
     DevBuf<long long> d_idx_off;
     std::vector<HostBatch> batches;
     struct Round { int level; size_t dev_off; int count; int max_m; };
-    std::vector<Round> rounds;      // extend-add rounds, sorted by level of the PARENT
+    std::vector<Round> rounds;      // assembly launches: the parents of each tree level (max_m = largest parent order)
     // device: values
     DevBuf<double> d_pool;
     long long pool_stride = 0;
@@ -386,37 +386,43 @@ struct Engine {
         batches = make_batches(S, flat);
         for (auto &b : batches) maxfb = std::max(maxfb, (int)b.ids.size());
 
-        // extend-add rounds: round r of level L = the r-th child of every parent at level L
+        // assembly: per tree level the parents that have children (one launch per level), and for every child the
+        // inverse of its relative map (parent local index -> child update index)
         rounds.clear();
-        std::vector<std::vector<std::vector<int> > > per_level(S.n_levels);
-        for (int p = 0; p < nf; ++p) {
-            const int64_t c0 = S.child_ptr[p], c1 = S.child_ptr[p + 1];
-            auto &lv = per_level[S.fronts[p].level];
-            if ((int64_t)lv.size() < c1 - c0) lv.resize(c1 - c0);
-            for (int64_t c = c0; c < c1; ++c) lv[c - c0].push_back(S.child_ids[c]);
-        }
-        for (int l = 0; l < S.n_levels; ++l)
-            for (auto &r : per_level[l]) {
-                // gridDim.y limit: split long rounds
-                for (size_t s0 = 0; s0 < r.size(); s0 += 32768) {
+        {
+            std::vector<std::vector<int> > per_level(S.n_levels);
+            for (int p = 0; p < nf; ++p)
+                if (S.child_ptr[p + 1] > S.child_ptr[p]) per_level[S.fronts[p].level].push_back(p);
+            for (int l = 0; l < S.n_levels; ++l) {
+                auto &r = per_level[l];
+                for (size_t s0 = 0; s0 < r.size(); s0 += 32768) {      // gridDim.y limit
                     Round rd;
                     rd.level = l;
                     rd.dev_off = flat.size();
                     rd.count = (int)std::min<size_t>(32768, r.size() - s0);
-                    rd.max_m = 0;
+                    rd.max_m = 0;                                       // here: largest parent order
                     for (int i = 0; i < rd.count; ++i) {
-                        rd.max_m = std::max(rd.max_m, S.fronts[r[s0 + i]].m);
+                        rd.max_m = std::max(rd.max_m, S.fronts[r[s0 + i]].f);
                         flat.push_back(r[s0 + i]);
                     }
                     rounds.push_back(rd);
                 }
             }
-        d_ids.upload(flat);
-        d_rel.upload(S.rel);
-        {
-            std::vector<long long> ro(S.rel_off.begin(), S.rel_off.end());
-            d_rel_off.upload(ro);
+            std::vector<long long> inv_off(nf + 1, 0);
+            for (int c = 0; c < nf; ++c)
+                inv_off[c + 1] = inv_off[c] + (S.fronts[c].parent >= 0 ? S.fronts[S.fronts[c].parent].f : 0);
+            std::vector<int> inv(inv_off[nf], -1);
+            for (int c = 0; c < nf; ++c) {
+                if (S.fronts[c].parent < 0) continue;
+                for (int jx = 0; jx < S.fronts[c].m; ++jx) inv[inv_off[c] + S.rel[S.rel_off[c] + jx]] = jx;
+            }
+            d_inv.upload(inv);
+            d_inv_off.upload(inv_off);
+            std::vector<long long> cp(S.child_ptr.begin(), S.child_ptr.end());
+            d_child_ptr.upload(cp);
+            d_child_ids.upload(S.child_ids);
         }
+        d_ids.upload(flat);
         d_fidx.upload(S.fidx);
         {
             std::vector<long long> io(nf);
@@ -664,8 +670,8 @@ struct Engine {
         size_t ri = 0, bi = 0;
         for (int l = 0; l < S.n_levels; ++l) {
             for (; ri < rounds.size() && rounds[ri].level == l; ++ri) {
-                ngt::launch_extend_add(c, d_ids.p + rounds[ri].dev_off, rounds[ri].count, rounds[ri].max_m, d_rel.p,
-                                       d_rel_off.p);
+                ngt::launch_assemble(c, d_ids.p + rounds[ri].dev_off, rounds[ri].count, rounds[ri].max_m, d_child_ptr.p,
+                                     d_child_ids.p, d_inv.p, d_inv_off.p);
                 st.n_launches++;
             }
             for (; bi < batches.size() && S.batches[bi].level == l; ++bi) eliminate(c, batches[bi], d_ids.p);

@@ -1073,39 +1073,48 @@ void launch_ingest_dense(double *pool, long long pool_stride, int nbatch, const 
 }
 
 // =====================================================================================================
-// assembly (extend-add): parent[rel[i], rel[j]] += child[k+i, k+j];  parent tau col += child delta-tau col
-// grid (row tiles of 8, child, network); threads sweep the columns (coalesced reads of the child)
+// assembly (extend-add), parent-centric gather: one warp per row of a parent front walks the parent's children in a
+// fixed order and adds the matching child entries (inv maps a parent local index to the child's update index or -1):
+//   parent[a, b] += child[k_c + inv[a], k_c + inv[b]],   parent[a, tau] += child[k_c + inv[a], tau]
+// Every parent entry has exactly one writer, so there are no atomics and the sum order is deterministic; parent rows
+// are written with unit stride.  grid (row tiles of 8, parents of the level, networks).
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
-extend_add_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, const int *rel,
-                  const long long *rel_off) {
-    const int cid = ids[blockIdx.y];
-    const DFront C = fronts[cid];
-    const int m = C.f - C.k;
-    const int i0 = blockIdx.x * 8;
-    if (i0 >= m) return;
-    const DFront Pf = fronts[C.parent];
+assemble_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, const long long *child_ptr,
+                const int *child_ids, const int *inv, const long long *inv_off) {
+    const int pid = ids[blockIdx.y];
+    const DFront P = fronts[pid];
+    const int a = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (a >= P.f) return;
+    const int lane = threadIdx.x & 31;
     double *base = pool + (long long)blockIdx.z * pool_stride;
-    const double *Cm = base + C.off;
-    double *Pm = base + Pf.off;
-    const int *rl = rel + rel_off[cid];
-    const int wr = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = i0 + wr;
-    if (i >= m) return;
-    const double *crow = Cm + (long long)(C.k + i) * C.ld + C.k;
-    double *prow = Pm + (long long)rl[i] * Pf.ld;
-    for (int jx = lane; jx <= m; jx += 32) {
-        const double v = crow[jx];
-        const int pc = (jx < m) ? rl[jx] : Pf.f;
-        if (v != 0.0) prow[pc] += v;
+    double *prow = base + P.off + (long long)a * P.ld;
+    for (long long ci = child_ptr[pid]; ci < child_ptr[pid + 1]; ++ci) {
+        const int cid = child_ids[ci];
+        const int *iv = inv + inv_off[cid];
+        const int ia = iv[a];
+        if (ia < 0) continue;                      // this child does not touch row a (uniform over the warp)
+        const DFront C = fronts[cid];
+        const double *crow = base + C.off + (long long)(C.k + ia) * C.ld + C.k;
+        for (int b = lane; b < P.f; b += 32) {
+            const int ib = iv[b];
+            if (ib >= 0) {
+                const double v = crow[ib];
+                if (v != 0.0) prow[b] += v;
+            }
+        }
+        if (lane == 0) {
+            const double v = crow[C.f - C.k];      // the child's delta-tau column
+            if (v != 0.0) prow[P.f] += v;
+        }
     }
 }
 
-void launch_extend_add(const LaunchCtx &c, const int *ids, int nchild, int max_m, const int *rel,
-                       const long long *rel_off) {
-    if (nchild <= 0 || max_m <= 0) return;
-    dim3 grid((max_m + 7) / 8, nchild, c.nbatch);
-    extend_add_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, rel, rel_off);
+void launch_assemble(const LaunchCtx &c, const int *ids, int nparents, int max_f, const long long *child_ptr,
+                     const int *child_ids, const int *inv, const long long *inv_off) {
+    if (nparents <= 0 || max_f <= 0) return;
+    dim3 grid((max_f + 7) / 8, nparents, c.nbatch);
+    assemble_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, child_ptr, child_ids, inv, inv_off);
 }
 
 // =====================================================================================================

@@ -137,10 +137,11 @@ void launch_ingest_sparse(double *pool, long long pool_stride, int nbatch, const
 void launch_ingest_dense(double *pool, long long pool_stride, int nbatch, const double *K, int n, const int *pos,
                          int nI, DFront f0, DFront root, double *tau0, int *errflag, cudaStream_t s);
 
-// ---- assembly: child update blocks (+ delta-tau column) are added into their parents ---------------
-// ids: children of one round (all have distinct parents); rel/rel_off: local index of child update row in parent
-void launch_extend_add(const LaunchCtx &c, const int *ids, int nchild, int max_m, const int *rel,
-                       const long long *rel_off);
+// ---- assembly: child update blocks (+ delta-tau column) are added into their parents -----------------------
+// ids: parents of one tree level; child_ptr/child_ids: CSR of children per front; inv/inv_off: per child, parent local
+// index -> child update index or -1
+void launch_assemble(const LaunchCtx &c, const int *ids, int nparents, int max_f, const long long *child_ptr,
+                     const int *child_ids, const int *inv, const long long *inv_off);
 
 // ---- phase 2: build one front per a in the group from the reduced root block -----------------------
 // group = [g0, g0+ng) rows of the root, other = the remaining root rows.  Task t (a = g0 + t) gets a front of
