@@ -676,6 +676,7 @@ struct Engine {
             }
             for (; bi < batches.size() && S.batches[bi].level == l; ++bi) eliminate(c, batches[bi], d_ids.p);
         }
+        CK(cudaGetLastError());     // a bad launch configuration must not pass silently
         if (!capturing) CK(cudaEventRecord(ev[2], stream));
         have_phase1 = true;
         have_phase2 = false;
@@ -741,6 +742,7 @@ struct Engine {
                                        rank, nranks);
             st.n_launches++;
         }
+        CK(cudaGetLastError());
         if (!capturing) CK(cudaEventRecord(ev[4], stream));
     }
 
@@ -1044,7 +1046,7 @@ struct Engine {
 Engine *make_engine(const ngt_options *opt, int64_t nbatch) {
     Engine *E = new Engine();
     if (opt) E->opt = *opt;
-    if (nbatch < 1) { delete E; throw InvalidError("nbatch must be >= 1"); }
+    if (nbatch < 1 || nbatch > 65535) { delete E; throw InvalidError("nbatch must be in 1..65535 (one grid dimension per network)"); }
     E->nbatch = (int)nbatch;
     return E;
 }
@@ -1054,7 +1056,7 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
     auto t0 = std::chrono::steady_clock::now();
     ngt::Timer tm;
     if (n <= 0 || nnz < 0) throw InvalidError("empty network");
-    if (n > 2000000000LL) throw InvalidError("too many nodes");
+    if (n > 2000000000LL || nnz > 2000000000LL) throw InvalidError("too many nodes or rates (32-bit entry indices)");
     E->n = n;
     E->nnz = nnz;
     E->dense = false;
