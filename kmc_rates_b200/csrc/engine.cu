@@ -170,6 +170,7 @@ struct Engine {
 
     // device: structure
     DevBuf<DFront> d_fronts;
+    std::vector<DFront> h_fronts, h_p2fronts;   // host mirrors (single-front launches pass the descriptor by value)
     DevBuf<int> d_ids;              // batch ids (phase 1), then extend-add rounds
     DevBuf<int> d_inv, d_child_ids;
     DevBuf<long long> d_inv_off, d_child_ptr;
@@ -382,6 +383,7 @@ struct Engine {
             hf[i].parent = S.fronts[i].parent;
         }
         d_fronts.upload(hf);
+        h_fronts = hf;
         std::vector<int> flat;
         batches = make_batches(S, flat);
         for (auto &b : batches) maxfb = std::max(maxfb, (int)b.ids.size());
@@ -490,6 +492,7 @@ struct Engine {
         }
         p2_stride = off;
         d_p2fronts.upload(pf);
+        h_p2fronts = pf;
         d_p2ids.upload(flat);
         d_p2pool.alloc((size_t)p2_stride * nbatch);
     }
@@ -535,8 +538,15 @@ struct Engine {
         const int nfb = (int)b.ids.size();
         const int tm = ngt::update_tile_m(opt.gemm_path), tn = ngt::update_tile_n(opt.gemm_path);
         const int *ids = dev_ids + b.dev_off;
+        // a launch that covers exactly one front carries its descriptor in the kernel parameters
+        const DFront *f0 = c.f0;
+        if (!f0 && nfb == 1) {
+            if (c.fronts == d_fronts.p && (size_t)b.ids[0] < h_fronts.size()) f0 = &h_fronts[b.ids[0]];
+            else if (c.fronts == d_p2fronts.p && (size_t)b.ids[0] < h_p2fronts.size()) f0 = &h_p2fronts[b.ids[0]];
+        }
         for (int j = 0; j < b.max_k; j += ngt::NB_INNER) {
             ngt::LaunchCtx cj = c;
+            cj.f0 = f0;
             if (wslot_per_step) cj.ko.wslot = (j % ngt::NB_OUTER) / ngt::NB_INNER;   // keep every W of the outer block
             int max_cols = 0;   // columns right of the panel incl. the tau column, widest live front
             for (int i = 0; i < nfb; ++i)
@@ -552,17 +562,38 @@ struct Engine {
                 st.n_launches++;
             }
             double fl = 0, dummy = 0;
-            const int ta = max_tiles(b, j, ngt::MODE_A, tm, tn, fl);
-            const int tb = max_tiles(b, j, ngt::MODE_B, tm, tn, fl);
-            const int td1a = max_tiles(b, j, ngt::MODE_D1A, tm, tn, fl);
-            const int td1b = max_tiles(b, j, ngt::MODE_D1B, tm, tn, fl);
+            int ta = max_tiles(b, j, ngt::MODE_A, tm, tn, fl);
+            int tb = max_tiles(b, j, ngt::MODE_B, tm, tn, fl);
+            int td1a = max_tiles(b, j, ngt::MODE_D1A, tm, tn, fl);
+            int td1b = max_tiles(b, j, ngt::MODE_D1B, tm, tn, fl);
             int td2 = max_tiles(b, j, ngt::MODE_D2, tm, tn, fl);
             st.schur_flops += fl * nbatch;
+            // launches that would fill less than one CTA slot per SM use half-height tiles (twice the CTAs): these
+            // thin updates are bound by each SM's L2 port, not by the tensor pipe
+            long long live_fronts = 0;
+            for (int i = 0; i < nfb; ++i) live_fronts += (b.k[i] > j);
+            auto half_tiles = [&](int tiles_full) {
+                return opt.gemm_path == 0 && tiles_full > 0 && (long long)tiles_full * live_fronts * nbatch < 148;
+            };
+            ngt::LaunchCtx c_ab = cj, c_d1 = cj;
+            if (half_tiles(ta + tb)) {
+                c_ab.tile_m = 64;
+                ta = max_tiles(b, j, ngt::MODE_A, 64, tn, dummy);
+                tb = max_tiles(b, j, ngt::MODE_B, 64, tn, dummy);
+            }
+            if (half_tiles(td1a + td1b)) {
+                c_d1.tile_m = 64;
+                td1a = max_tiles(b, j, ngt::MODE_D1A, 64, tn, dummy);
+                td1b = max_tiles(b, j, ngt::MODE_D1B, 64, tn, dummy);
+            }
+            const bool d2_half = half_tiles(td2);
+            if (d2_half) td2 = max_tiles(b, j, ngt::MODE_D2, 64, tn, dummy);
             // large trailing regions run on the 128 x 128 kernel when they fill the machine (>= 2 waves of big
             // tiles); small regions keep the 128 x 64 kernel (more CTAs)
             ngt::LaunchCtx c2 = cj;
+            if (d2_half) c2.tile_m = 64;
             bool d2_async = false;
-            if (td2 > 0) {
+            if (td2 > 0 && !d2_half) {
                 long long live = 0;
                 for (int i = 0; i < nfb; ++i) live += (b.k[i] > j);
                 const int tbig = max_tiles(b, j, ngt::MODE_D2, ngt::update_tile_m(2), ngt::update_tile_n(2), dummy);
@@ -584,7 +615,7 @@ struct Engine {
                 st.n_launches++;
                 st.reserved[0] += 1;   // Schur-update launches
             };
-            if (ta + tb > 0) timed(stream, [&] { ngt::launch_update(cj, ids, nfb, j, ngt::MODE_AB, ta + tb, ta); });
+            if (ta + tb > 0) timed(stream, [&] { ngt::launch_update(c_ab, ids, nfb, j, ngt::MODE_AB, ta + tb, ta); });
             if (td1a + td1b + td2 > 0) {
                 if (d2_async) {
                     // D2 needs the finished panels of this outer block ...
@@ -594,10 +625,10 @@ struct Engine {
                 if (td1a + td1b > 0) {
                     // ... D1 touches the region the previous D2 was writing
                     if (d2_pending) { CK(cudaStreamWaitEvent(stream, sync_event(1), 0)); d2_pending = false; }
-                    timed(stream, [&] { ngt::launch_update(cj, ids, nfb, j, ngt::MODE_D1, td1a + td1b, td1a); });
+                    timed(stream, [&] { ngt::launch_update(c_d1, ids, nfb, j, ngt::MODE_D1, td1a + td1b, td1a); });
                 }
                 if (td2 > 0) {
-                    const bool via_tmap = use_tmap && have_tmaps && opt.gemm_path == 0 && c2.gemm_path == 0 && nfb == 1 &&
+                    const bool via_tmap = !d2_half && use_tmap && have_tmaps && opt.gemm_path == 0 && c2.gemm_path == 0 && nfb == 1 &&
                                           c.fronts == d_fronts.p && b.ids[0] == 0 && tma_eligible(b, 0, j, ngt::MODE_D2);
                     if (d2_async) {
                         c2.stream = stream2;
@@ -912,6 +943,7 @@ struct Engine {
         HostBatch hb;
         hb.ids = {0}; hb.f = {P.f}; hb.k = {P.k}; hb.fr = {fr}; hb.max_k = kb; hb.dev_off = 0;
         ngt::LaunchCtx c = ctx(d_pool.p, pool_stride, d_dfronts.p);
+        c.f0 = &P;
         wslot_per_step = true;
         const bool la = use_lookahead;
         use_lookahead = false;
@@ -957,6 +989,7 @@ struct Engine {
         const int tm = ngt::update_tile_m(opt.gemm_path), tn = ngt::update_tile_n(opt.gemm_path);
         ngt::LaunchCtx c = ctx(d_pool.p, pool_stride, d_dfronts.p);
         c.ko = own();
+        c.f0 = &B;
         const int *ids = d_dids.p + 1 + par;
         double fl = 0;
         for (int j = J; j < JE; j += ngt::NB_INNER) {

@@ -5,12 +5,90 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace ngt {
 
 // =====================================================================================================
 // helpers
 // =====================================================================================================
+// Programmatic dependent launch: every kernel on the elimination chain waits for its predecessor (first thing, in
+// every CTA, before any early exit) and then lets its successor start launching, so the launch latency of the next
+// kernel overlaps this kernel's execution instead of adding to the chain.  A successor's CTAs do nothing before
+// their own wait returns (= this grid complete and flushed), so ordering and memory visibility are those of ordinary
+// stream order.  (Triggering before the wait pipelines launches deeper but measured slower on the config 2 step:
+// 5.73 vs 5.58 ms.)  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+static bool use_pdl() {
+    static const bool on = std::getenv("NGT_B200_NO_PDL") == nullptr;
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+static void launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    if (use_pdl()) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+    }
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+// single-front launches carry their front descriptor in the kernel parameters (saves two dependent global loads)
+__device__ __forceinline__ DFront fetch_front(const DFront *fronts, const int *ids, int slot, const DFront &F0, int has_f0) {
+    return has_f0 ? F0 : fronts[ids[slot]];
+}
+
+// FP64 tensor-core MMA, C(8x8) += A(8x4) B(4x8): lane (g = lane/4, t = lane%4) holds A[g][t], B[t][g], C[g][2t..2t+1].
+// On B200 the vector FP64 pipe issues one warp DFMA per 8 cycles per scheduler (16 FMA/clk/SM, measured with
+// tools/lat_bench.cu); DMMA runs at ~62 FMA/clk/SM, so every product with a GEMM shape goes through it.
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// U' = W X for one slab of a row panel, on the tensor cores.  Wd: W, 32 x 32 with row stride WD_LD; xs: the slab,
+// 32 x CW with row stride CW + 4 (both strides = 4 mod 16 doubles: conflict-free fragment loads).  Warps take column
+// groups of 8 round-robin; the result goes straight to global memory (rows < nbp, columns < ncols_live).
+constexpr int WD_LD = NB_INNER + 4;
+template <int CW, int NWARPS>
+__device__ __forceinline__ void rowpanel_slab_mma(const double *Wd, const double *xs, double *Mout, long long ld,
+                                                  int nbp, int ncols_live, int warp, int lane) {
+    const int g = lane >> 2, t4 = lane & 3;
+    for (int nt = warp; nt < CW / 8; nt += NWARPS) {
+        if (nt * 8 >= ncols_live) break;
+        double acc[4][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) acc[mi][0] = acc[mi][1] = 0.0;
+#pragma unroll
+        for (int k4 = 0; k4 < NB_INNER / 4; ++k4) {
+            const double b = xs[(k4 * 4 + t4) * (CW + 4) + nt * 8 + g];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) dmma884(acc[mi][0], acc[mi][1], Wd[(mi * 8 + g) * WD_LD + k4 * 4 + t4], b);
+        }
+        const int c = nt * 8 + 2 * t4;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const int r = mi * 8 + g;
+            if (r < nbp) {
+                if (c < ncols_live) Mout[(long long)r * ld + c] = acc[mi][0];
+                if (c + 1 < ncols_live) Mout[(long long)r * ld + c + 1] = acc[mi][1];
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -23,8 +101,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 // =====================================================================================================
 __global__ void __launch_bounds__(1024)
 rowsum_kernel(const double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j,
-              double *rsbuf, int maxfb, int maxchunks) {
-    const DFront F = fronts[ids[blockIdx.y]];
+              double *rsbuf, int maxfb, int maxchunks, DFront F0, int has_f0) {
+    pdl_enter();
+    const DFront F = fetch_front(fronts, ids, blockIdx.y, F0, has_f0);
     if (j >= F.k) return;
     const int nbp = min(NB_INNER, F.k - j);
     const int je = j + nbp;
@@ -47,314 +126,315 @@ rowsum_kernel(const double *pool, long long pool_stride, const DFront *fronts, c
 
 void launch_rowsum(const LaunchCtx &c, const int *ids, int nfb, int j, int max_cols) {
     dim3 grid((max_cols + RS_CHUNK - 1) / RS_CHUNK, nfb, c.nbatch);
-    rowsum_kernel<<<grid, 1024, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.rsbuf, c.maxfb, c.maxchunks);
+    launch_chain(rowsum_kernel, grid, dim3(1024), 0, c.stream, c.pool, c.pool_stride, c.fronts, ids, j, c.rsbuf, c.maxfb,
+                 c.maxchunks, c.f0 ? *c.f0 : DFront{}, c.f0 ? 1 : 0);
 }
 
 // =====================================================================================================
-// panel kernel: one CTA (1024 threads, thread (u,q) owns T[u][q] and G[u][q] in registers) per front and network.
-//   s_u  = sum_{v >= je} P[j+u, v]                (mass leaving the panel; GTH row sums)
-//   W    = (I - P_XX)^-1 by subtraction-free Gauss-Jordan; pivot d_p = sum_{q != p} T[p,q] + s_p.
-// Row p is published to shared memory (double buffered) by its own warp one step ahead, together with 1/d_p,
-// so a step costs one barrier, one shuffle and three FMAs for everybody else.
-// Fronts with few columns also apply W to their row panel here (U' = W [P_XR | tau_X]).
+// panel kernel: one CTA per front and network.
+//   s_u  = sum_{v >= je} P[j+u, v]                (mass leaving the panel; GTH row sums)     -- all warps
+//   W    = (I - P_XX)^-1 by subtraction-free Gauss-Jordan; pivot d_p = sum_{q > p} T[p,q] + s_p  -- 4 warps
+//   U'   = W [P_XR | tau_X] for fronts with few columns                                        -- all warps
+// Gauss-Jordan layout: 4 warps x 32 lanes, lane u = row u, warp w = columns 8w..8w+7, in place in registers: at
+// step p columns < p hold the accumulated inverse G, columns > p the remaining T.  T[u][u] is never used: the
+// self-loop mass is discarded and every pivot is re-summed from off-diagonal entries only, which keeps the
+// recurrence free of subtractions.
+// The 32-step dependency chain is kept short by computing the NEXT pivot one step ahead:
+//     d_{p+1} = A + f B,   A = sum_{q>p+1} T[p+1][q] + s_{p+1},  B = sum_{q>p+1} T[p][q] + s_p,  f = T[p+1][p] / d_p
+// (the same non-negative terms, grouped so that A and B are known before 1/d_p is).  Every thread evaluates this
+// scalar recurrence redundantly, so the chain reciprocal -> multiply -> fma -> reciprocal never leaves the
+// register file; rows, columns and partial sums are handed over through double-buffered shared memory with one
+// named barrier per step, off the chain.
+// NT = 512: single-front launches at the top of the assembly tree (16 warps share the row sums and the row panel);
+// NT = 128: launches with many fronts (leaf levels, batched networks, phase-2 tasks), 4 CTAs per SM.
 // =====================================================================================================
-__global__ void __launch_bounds__(1024, 1)
+constexpr int GJ_WARPS = 4, GJ_COLS = NB_INNER / GJ_WARPS;
+
+// X[i] with a warp-uniform runtime i, without demoting the register array to local memory
+__device__ __forceinline__ double gj_get(const double (&X)[GJ_COLS], int i) {
+    double v = X[0];
+    switch (i) {
+        case 1: v = X[1]; break; case 2: v = X[2]; break; case 3: v = X[3]; break; case 4: v = X[4]; break;
+        case 5: v = X[5]; break; case 6: v = X[6]; break; case 7: v = X[7]; break; default: break;
+    }
+    return v;
+}
+__device__ __forceinline__ void gj_set(double (&X)[GJ_COLS], int i, double v) {
+    switch (i) {
+        case 0: X[0] = v; break; case 1: X[1] = v; break; case 2: X[2] = v; break; case 3: X[3] = v; break;
+        case 4: X[4] = v; break; case 5: X[5] = v; break; case 6: X[6] = v; break; default: X[7] = v; break;
+    }
+}
+// sum of the local columns i >= t (t warp-uniform), fixed summation tree
+__device__ __forceinline__ double gj_tail_sum(const double (&X)[GJ_COLS], int t) {
+    double m[GJ_COLS];
+#pragma unroll
+    for (int i = 0; i < GJ_COLS; ++i) m[i] = (i >= t) ? X[i] : 0.0;
+    return ((m[0] + m[1]) + (m[2] + m[3])) + ((m[4] + m[5]) + (m[6] + m[7]));
+}
+__device__ __forceinline__ void gj_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(GJ_WARPS * 32) : "memory"); }
+
+#ifdef NGT_PANEL_CLOCKS
+__device__ long long g_panel_clk[8];
+__device__ long long g_gj_clk[8];
+#define NGT_CLK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_panel_clk[i] = clock64(); } while (0)
+#define NGT_GJ_T(i) do { const long long t_ = clock64(); gj_acc[i] += t_ - gj_last; gj_last = t_; } while (0)
+#else
+#define NGT_CLK(i) do { } while (0)
+#define NGT_GJ_T(i) do { } while (0)
+#endif
+
+template <int NT>
+__global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 4))
 panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j,
-             double *wbuf, const double *rsbuf, int maxfb, int maxchunks, int *errflag, KOpt ko) {
-    const DFront F = fronts[ids[blockIdx.x]];
+             double *wbuf, const double *rsbuf, int maxfb, int maxchunks, int *errflag, KOpt ko, DFront F0, int has_f0) {
+    pdl_enter();
+    constexpr int NW = NT / 32;              // warps
+    constexpr int CW = 64;                   // row-panel columns per slab
+    const DFront F = fetch_front(fronts, ids, blockIdx.x, F0, has_f0);
     if (j >= F.k) return;
     double *M = pool + (long long)blockIdx.y * pool_stride + F.off;
     const int nbp = min(NB_INNER, F.k - j);
     const int je = j + nbp;
-    const int u = threadIdx.x >> 5, q = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    __shared__ double rowT[2][NB_INNER];
-    __shared__ double rowG[2][NB_INNER];
-    __shared__ double rowS[2], rowRD[2];
-    __shared__ double Ds[NB_INNER];
-    __shared__ double Ws[NB_INNER][NB_INNER];
-    __shared__ double xs[NB_INNER][128];
+    __shared__ double Xs[NB_INNER][NB_INNER + 1];   // T on the way in, W on the way out (padded: lane = row access)
+    __shared__ double Ss[NB_INNER];
+    // Gauss-Jordan hand-over, double buffered by step parity: pivot row, pivot column, s of every row and the
+    // per-warp partial sums of every row over the columns two past the pivot
+    __shared__ __align__(16) double Row[2][NB_INNER], Col[2][NB_INNER], Sv[2][NB_INNER], Ps[2][GJ_WARPS][NB_INNER];
+    __shared__ double D0;
+    __shared__ double xs[NB_INNER * (CW + 4)];
+    __shared__ double Wd[NB_INNER * WD_LD];
+    NGT_CLK(0);
 
-    // row sums over everything to the right of the panel (tau column excluded)
-    double s = 1.0;   // padding rows behave like isolated absorbing nodes
-    if (u < nbp) {
-        if (F.f - je > RS_SPLIT) {
+    // row sums over everything to the right of the panel (tau column excluded) and the T block.  A warp owns rows
+    // warp, warp + NW, ...; their loads are issued together so one round of memory latency covers all of them.
+    {
+        constexpr int RPW = NB_INNER / NW;
+        double s0[RPW], s1[RPW], s2[RPW], s3[RPW];
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) s0[i] = s1[i] = s2[i] = s3[i] = 0.0;
+        const bool wide = F.f - je > RS_SPLIT;
+        if (wide) {
             const int nch = (F.f - je + RS_CHUNK - 1) / RS_CHUNK;
             const double *rs = rsbuf + (((long long)blockIdx.y * maxfb + blockIdx.x) * maxchunks) * NB_INNER;
-            s = 0.0;
-            for (int ch = q; ch < nch; ch += 32) s += rs[ch * NB_INNER + u];
-            s = warp_sum(s);
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) {
+                const int u = warp + i * NW;
+                if (u < nbp)
+                    for (int ch = lane; ch < nch; ch += 32) s0[i] += rs[ch * NB_INNER + u];
+            }
         } else {
-            const double *row = M + (long long)(j + u) * F.ld;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int c = je + q;
-            for (; c + 96 < F.f; c += 128) { s0 += row[c]; s1 += row[c + 32]; s2 += row[c + 64]; s3 += row[c + 96]; }
-            for (; c < F.f; c += 32) s0 += row[c];
-            s = warp_sum((s0 + s1) + (s2 + s3));
-        }
-    }
-    double t = (u < nbp && q < nbp && u != q) ? M[(long long)(j + u) * F.ld + j + q] : 0.0;
-    double g = (u == q) ? 1.0 : 0.0;
-    if (u == 0) {
-        const double d = warp_sum(t) + s;
-        rowT[0][q] = t;
-        rowG[0][q] = g;
-        if (q == 0) {
-            rowS[0] = s;
-            rowRD[0] = 1.0 / d;
-            Ds[0] = d;
-            if (!(d > 0.0) || isinf(d)) atomicOr(errflag, 1);
-        }
-    }
-    for (int p = 0; p < nbp; ++p) {
-        __syncthreads();
-        const int b = p & 1;
-        if (u != p) {
-            const double tp = rowT[b][q], gp = rowG[b][q], sp = rowS[b], rd = rowRD[b];
-            const double tup = __shfl_sync(0xffffffffu, t, p);
-            const double fup = (tup == 0.0) ? 0.0 : tup * rd;   // rows that do not reach p stay clean even if d == 0
-            t = (q == p || q == u) ? 0.0 : fma(fup, tp, t);
-            g = fma(fup, gp, g);
-            s = fma(fup, sp, s);
-            if (u == p + 1 && u < nbp) {          // publish the next pivot row one step ahead
-                const double d = warp_sum(t) + s;
-                rowT[b ^ 1][q] = t;
-                rowG[b ^ 1][q] = g;
-                if (q == 0) {
-                    rowS[b ^ 1] = s;
-                    rowRD[b ^ 1] = 1.0 / d;
-                    Ds[u] = d;
-                    if (!(d > 0.0) || isinf(d)) atomicOr(errflag, 1);
+            const double *base = M + (long long)j * F.ld;
+            int c = je + lane;
+            for (; c + 96 < F.f; c += 128) {
+#pragma unroll
+                for (int i = 0; i < RPW; ++i) {
+                    const int u = warp + i * NW;
+                    if (u < nbp) {
+                        const double *row = base + (long long)u * F.ld;
+                        s0[i] += row[c]; s1[i] += row[c + 32]; s2[i] += row[c + 64]; s3[i] += row[c + 96];
+                    }
+                }
+            }
+            for (; c < F.f; c += 32) {
+#pragma unroll
+                for (int i = 0; i < RPW; ++i) {
+                    const int u = warp + i * NW;
+                    if (u < nbp) s0[i] += base[(long long)u * F.ld + c];
                 }
             }
         }
-    }
-    __syncthreads();
-    const double w = (u < nbp) ? g / Ds[u] : 0.0;
-    Ws[u][q] = w;
-    wbuf[((long long)blockIdx.y * maxfb + blockIdx.x + ko.wslot) * (NB_INNER * NB_INNER) + u * NB_INNER + q] = w;
-
-    // fused row panel for narrow fronts: columns je..f (f = tau column) in slabs of 128 staged through smem
-    const int ncols = F.f + 1 - je;
-    if (ncols > ko.fuse_cols) return;
-    const int cc = threadIdx.x & 127, r0 = threadIdx.x >> 7;
-    for (int cs = 0; cs < ncols; cs += 128) {
-        __syncthreads();
-        const bool live = cs + cc < ncols;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = r0 + 8 * i;
-            xs[r][cc] = (live && r < nbp) ? M[(long long)(j + r) * F.ld + je + cs + cc] : 0.0;
-        }
-        __syncthreads();
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
-        for (int tt = 0; tt < NB_INNER; ++tt) {
-            const double x = xs[tt][cc];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = fma(Ws[r0 + 8 * i][tt], x, acc[i]);
-        }
-        if (live) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = r0 + 8 * i;
-                if (r < nbp) M[(long long)(j + r) * F.ld + je + cs + cc] = acc[i];
-            }
-        }
-    }
-}
-
-// =====================================================================================================
-// throughput variant of the panel kernel for launches with many fronts (leaf levels, batched networks, phase-2
-// tasks): 256 threads, each thread owns 4 columns of one row, so 4+ panels are resident per SM and their
-// latency-bound Gauss-Jordan chains overlap.  Same arithmetic, same order of operations per element.
-// =====================================================================================================
-__global__ void __launch_bounds__(256, 4)
-panel_tp_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j,
-                double *wbuf, const double *rsbuf, int maxfb, int maxchunks, int *errflag, KOpt ko) {
-    const DFront F = fronts[ids[blockIdx.x]];
-    if (j >= F.k) return;
-    double *M = pool + (long long)blockIdx.y * pool_stride + F.off;
-    const int nbp = min(NB_INNER, F.k - j);
-    const int je = j + nbp;
-    const int u = threadIdx.x >> 3, cg = threadIdx.x & 7, q0 = cg * 4;
-    const int lane = threadIdx.x & 31;
-
-    __shared__ double rowT[2][NB_INNER];
-    __shared__ double rowG[2][NB_INNER];
-    __shared__ double rowS[2], rowRD[2];
-    __shared__ double Ds[NB_INNER];
-    __shared__ double Ws[NB_INNER][NB_INNER];
-    __shared__ double xs[NB_INNER][64];
-
-    auto group_sum = [](double v) {   // sum over the 8 lanes that share a row
-        v += __shfl_xor_sync(0xffffffffu, v, 4, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 2, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 1, 8);
-        return v;
-    };
-
-    // NOTE: four rows share a warp here, so every shuffle below is executed by all 32 lanes unconditionally
-    // (rows beyond nbp contribute zeros); only the use of the result is predicated.
-    double s = 0.0;
-    {
-        const bool live_row = u < nbp;
-        if (F.f - je > RS_SPLIT) {
-            const int nch = (F.f - je + RS_CHUNK - 1) / RS_CHUNK;
-            const double *rs = rsbuf + (((long long)blockIdx.y * maxfb + blockIdx.x) * maxchunks) * NB_INNER;
-            if (live_row)
-                for (int ch = cg; ch < nch; ch += 8) s += rs[ch * NB_INNER + u];
-        } else if (live_row) {
-            const double *row = M + (long long)(j + u) * F.ld;
-            double s0 = 0.0, s1 = 0.0;
-            int c = je + cg;
-            for (; c + 8 < F.f; c += 16) { s0 += row[c]; s1 += row[c + 8]; }
-            for (; c < F.f; c += 8) s0 += row[c];
-            s = s0 + s1;
-        }
-        s = group_sum(s);
-        if (!live_row) s = 1.0;   // padding rows behave like isolated absorbing nodes
-    }
-    double t[4], g[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int q = q0 + e;
-        t[e] = (u < nbp && q < nbp && u != q) ? M[(long long)(j + u) * F.ld + j + q] : 0.0;
-        g[e] = (u == q) ? 1.0 : 0.0;
-    }
-    {
-        const double d = group_sum((t[0] + t[1]) + (t[2] + t[3])) + s;
-        if (u == 0) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { rowT[0][q0 + e] = t[e]; rowG[0][q0 + e] = g[e]; }
-            if (cg == 0) {
-                rowS[0] = s;
-                rowRD[0] = 1.0 / d;
-                Ds[0] = d;
-                if (!(d > 0.0) || isinf(d)) atomicOr(errflag, 1);
-            }
-        }
-    }
-    for (int p = 0; p < nbp; ++p) {
-        __syncthreads();
-        const int b = p & 1;
-        // T[u][p] lives in element p&3 of the lane with column group p>>2
-        const int pe = p & 3;
-        const double mine = pe == 0 ? t[0] : pe == 1 ? t[1] : pe == 2 ? t[2] : t[3];
-        const double tup = __shfl_sync(0xffffffffu, mine, (lane & ~7) | (p >> 2));
-        if (u != p) {
-            const double sp = rowS[b], rd = rowRD[b];
-            const double fup = (tup == 0.0) ? 0.0 : tup * rd;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int q = q0 + e;
-                t[e] = (q == p || q == u) ? 0.0 : fma(fup, rowT[b][q], t[e]);
-                g[e] = fma(fup, rowG[b][q], g[e]);
-            }
-            s = fma(fup, sp, s);
-        }
-        const double d = group_sum((t[0] + t[1]) + (t[2] + t[3])) + s;   // all lanes, see NOTE
-        if (u == p + 1 && u < nbp) {          // publish the next pivot row one step ahead
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { rowT[b ^ 1][q0 + e] = t[e]; rowG[b ^ 1][q0 + e] = g[e]; }
-            if (cg == 0) {
-                rowS[b ^ 1] = s;
-                rowRD[b ^ 1] = 1.0 / d;
-                Ds[u] = d;
-                if (!(d > 0.0) || isinf(d)) atomicOr(errflag, 1);
+        for (int i = 0; i < RPW; ++i) {
+            const int u = warp + i * NW;
+            double sum = wide ? warp_sum(s0[i]) : warp_sum((s0[i] + s1[i]) + (s2[i] + s3[i]));
+            if (u >= nbp) sum = 1.0;   // padding rows behave like isolated absorbing nodes
+            const double t = (u < nbp && lane < nbp && lane != u) ? M[(long long)(j + u) * F.ld + j + lane] : 0.0;
+            Xs[u][lane] = t;
+            if (lane == 0) Ss[u] = sum;
+            if (u == 0) {                       // first pivot, summed directly
+                const double d0 = warp_sum(t) + sum;
+                if (lane == 0) D0 = d0;
             }
         }
     }
     __syncthreads();
-    double *Wout = wbuf + ((long long)blockIdx.y * maxfb + blockIdx.x + ko.wslot) * (NB_INNER * NB_INNER);
+    NGT_CLK(1);
+
+    if (warp < GJ_WARPS) {
+        const int c0 = warp * GJ_COLS;
+        double X[GJ_COLS];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const double w = (u < nbp) ? g[e] / Ds[u] : 0.0;
-        Ws[u][q0 + e] = w;
-        Wout[u * NB_INNER + q0 + e] = w;
-    }
-    const int ncols = F.f + 1 - je;
-    if (ncols > ko.fuse_cols) return;
-    const int cc = threadIdx.x & 63, r0 = threadIdx.x >> 6;
-    for (int cs = 0; cs < ncols; cs += 64) {
-        __syncthreads();
-        const bool live = cs + cc < ncols;
+        for (int i = 0; i < GJ_COLS; ++i) X[i] = Xs[lane][c0 + i];
+        double s = Ss[lane];
+        double RD = 0.0;
+        double dcur = D0, rd = 1.0 / dcur;     // d_p and 1/d_p of the current step, identical in every thread
+        // state before step 0, published like the end of a step
+        if (lane == 0) {
+            double2 *dst = reinterpret_cast<double2 *>(&Row[0][c0]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = r0 + 4 * i;
-            xs[r][cc] = (live && r < nbp) ? M[(long long)(j + r) * F.ld + je + cs + cc] : 0.0;
+            for (int i = 0; i < GJ_COLS / 2; ++i) dst[i] = make_double2(X[2 * i], X[2 * i + 1]);
         }
-        __syncthreads();
-        double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-        for (int tt = 0; tt < NB_INNER; ++tt) {
-            const double x = xs[tt][cc];
+        if (warp == 0) { Col[0][lane] = X[0]; Sv[0][lane] = s; }
+        Ps[0][warp][lane] = gj_tail_sum(X, 2 - c0);
+#ifdef NGT_PANEL_CLOCKS
+        long long gj_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, gj_last = clock64();
+#endif
+#pragma unroll 1
+        for (int p = 0; p < nbp; ++p) {
+            gj_barrier();
+            NGT_GJ_T(0);
+            const int b = p & 1, nb = b ^ 1;
+            const int p1 = min(p + 1, NB_INNER - 1);
+            // hand-over of state p-1: pivot row (own columns), pivot column (own row), s of the pivot row
+            double xp[GJ_COLS];
+            {
+                const double2 *src = reinterpret_cast<const double2 *>(&Row[b][c0]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fma(Ws[r0 + 4 * i][tt], x, acc[i]);
-        }
-        if (live) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = r0 + 4 * i;
-                if (r < nbp) M[(long long)(j + r) * F.ld + je + cs + cc] = acc[i];
+                for (int i = 0; i < GJ_COLS / 2; ++i) { const double2 v = src[i]; xp[2 * i] = v.x; xp[2 * i + 1] = v.y; }
             }
+            const double colv = Col[b][lane];
+            const double sp = Sv[b][p];
+            NGT_GJ_T(1);
+            // next pivot, one step ahead (see header)
+            const double A = ((Ps[b][0][p1] + Ps[b][1][p1]) + (Ps[b][2][p1] + Ps[b][3][p1])) + Sv[b][p1];
+            const double B = ((Ps[b][0][p] + Ps[b][1][p]) + (Ps[b][2][p] + Ps[b][3][p])) + sp;
+            const double cn = Col[b][p1];
+            const double fn = (cn == 0.0) ? 0.0 : cn * rd;
+            const double dn = fma(fn, B, A);
+            const double rdn = 1.0 / dn;
+            NGT_GJ_T(2);
+            if (threadIdx.x == 0 && (!(dcur > 0.0) || isinf(dcur))) atomicOr(errflag, 1);
+            if (lane == p) RD = rd;
+            // eliminate pivot p from every row; rows that do not reach p stay clean even if d_p == 0
+            const double f = (lane == p || colv == 0.0) ? 0.0 : colv * rd;
+#pragma unroll
+            for (int i = 0; i < GJ_COLS; ++i) X[i] = fma(f, xp[i], X[i]);
+            s = fma(f, sp, s);
+            if (warp == (p >> 3)) gj_set(X, p & 7, (lane == p) ? 1.0 : f);   // column p joins the inverse
+            NGT_GJ_T(3);
+            // publish state p for step p+1 (row p+1, column p+1, s) and step p+2 (partial sums past column p+2)
+            if (lane == p + 1) {
+                double2 *dst = reinterpret_cast<double2 *>(&Row[nb][c0]);
+#pragma unroll
+                for (int i = 0; i < GJ_COLS / 2; ++i) dst[i] = make_double2(X[2 * i], X[2 * i + 1]);
+            }
+            if (warp == (p1 >> 3)) Col[nb][lane] = gj_get(X, p1 & 7);
+            if (warp == 0) Sv[nb][lane] = s;
+            Ps[nb][warp][lane] = gj_tail_sum(X, p + 3 - c0);
+            rd = rdn;
+            dcur = dn;
+            NGT_GJ_T(4);
         }
+#ifdef NGT_PANEL_CLOCKS
+        if (threadIdx.x == 0 && blockIdx.x == 0)
+            for (int i = 0; i < 8; ++i) g_gj_clk[i] = gj_acc[i];
+#endif
+        NGT_CLK(2);
+        // W[u][q] = G[u][q] / d_u
+        if (lane >= nbp) RD = 0.0;
+#pragma unroll
+        for (int i = 0; i < GJ_COLS; ++i) Xs[lane][c0 + i] = (c0 + i < nbp) ? X[i] * RD : 0.0;
     }
+    __syncthreads();
+    NGT_CLK(3);
+    {
+        double *Wout = wbuf + ((long long)blockIdx.y * maxfb + blockIdx.x + ko.wslot) * (NB_INNER * NB_INNER);
+        for (int i = threadIdx.x; i < NB_INNER * NB_INNER; i += NT) Wout[i] = Xs[i >> 5][i & 31];
+    }
+
+    // fused row panel for narrow fronts: columns je..f (f = tau column) in slabs of CW staged through smem
+    const int ncols = F.f + 1 - je;
+    NGT_CLK(4);
+    if (ncols > ko.fuse_cols) return;
+    for (int i = threadIdx.x; i < NB_INNER * NB_INNER; i += NT) Wd[(i >> 5) * WD_LD + (i & 31)] = Xs[i >> 5][i & 31];
+    for (int cs = 0; cs < ncols; cs += CW) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < NB_INNER * CW; i += NT) {
+            const int r = i / CW, cc = i % CW;
+            xs[r * (CW + 4) + cc] = (cs + cc < ncols && r < nbp) ? M[(long long)(j + r) * F.ld + je + cs + cc] : 0.0;
+        }
+        __syncthreads();
+        rowpanel_slab_mma<CW, NW>(Wd, xs, M + (long long)j * F.ld + je + cs, F.ld, nbp, min(CW, ncols - cs), warp, lane);
+    }
+    NGT_CLK(5);
 }
 
 void launch_panel(const LaunchCtx &c, const int *ids, int nfb, int j) {
     dim3 grid(nfb, c.nbatch);
     if ((long long)nfb * c.nbatch >= 2 * 148)   // many panels: favour occupancy over single-panel latency
-        panel_tp_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.rsbuf, c.maxfb,
-                                                   c.maxchunks, c.errflag, c.ko);
+        launch_chain(panel_kernel<128>, grid, dim3(128), 0, c.stream, c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.rsbuf,
+                     c.maxfb, c.maxchunks, c.errflag, c.ko, c.f0 ? *c.f0 : DFront{}, c.f0 ? 1 : 0);
     else
-        panel_kernel<<<grid, 1024, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.rsbuf, c.maxfb,
-                                                 c.maxchunks, c.errflag, c.ko);
+        launch_chain(panel_kernel<512>, grid, dim3(512), 0, c.stream, c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.rsbuf,
+                     c.maxfb, c.maxchunks, c.errflag, c.ko, c.f0 ? *c.f0 : DFront{}, c.f0 ? 1 : 0);
 }
 
 // =====================================================================================================
-// row panel for wide fronts: U' = W [P_XR | tau_X] in place, columns je..f (f = tau column)
-// 256 threads handle 128 columns: thread (h = tid/128, col = tid%128) produces rows 16h..16h+15
+// row panel for wide fronts: U' = W [P_XR | tau_X] in place, columns je..f (f = tau column), on the tensor cores.
+// One CTA (8 warps) per slab of 64 columns: stage W and the slab in shared memory, one 32 x 8 x 32 DMMA product per warp.
 // =====================================================================================================
+constexpr int RP_CW = 64;
 __global__ void __launch_bounds__(256)
 rowpanel_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j,
-                const double *wbuf, int maxfb, KOpt ko) {
-    const DFront F = fronts[ids[blockIdx.y]];
+                const double *wbuf, int maxfb, KOpt ko, DFront F0, int has_f0) {
+    pdl_enter();
+    const DFront F = fetch_front(fronts, ids, blockIdx.y, F0, has_f0);
     if (j >= F.k) return;
     const int nbp = min(NB_INNER, F.k - j);
     const int je = j + nbp;
-    if (F.f + 1 - je <= ko.fuse_cols) return;    // done inside the panel kernel
-    const int col = je + blockIdx.x * 128 + (threadIdx.x & 127);
-    if (je + (int)blockIdx.x * 128 > F.f) return;
+    const int ncols = F.f + 1 - je;
+    if (ncols <= ko.fuse_cols) return;    // done inside the panel kernel
+    const int cs = blockIdx.x * RP_CW;
+    if (cs >= ncols) return;
     double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
 
-    __shared__ double Ws[NB_INNER][NB_INNER];
+    __shared__ double Wd[NB_INNER * WD_LD];
+    __shared__ double xs[NB_INNER * (RP_CW + 4)];
     const double *W = wbuf + ((long long)blockIdx.z * maxfb + blockIdx.y + ko.wslot) * (NB_INNER * NB_INNER);
-    for (int i = threadIdx.x; i < NB_INNER * NB_INNER; i += 256) Ws[i / NB_INNER][i % NB_INNER] = W[i];
-
-    double x[NB_INNER];
-    const bool live = col <= F.f && owned_col(ko, col, F.f);
-#pragma unroll
-    for (int r = 0; r < NB_INNER; ++r) x[r] = (live && r < nbp) ? M[(long long)(j + r) * F.ld + col] : 0.0;
-    __syncthreads();
-    const int h = threadIdx.x >> 7;
-    if (live) {
-#pragma unroll 4
-        for (int rr = 0; rr < 16; ++rr) {
-            const int r = h * 16 + rr;
-            if (r >= nbp) break;
-            double acc = 0.0;
-#pragma unroll
-            for (int t = 0; t < NB_INNER; ++t) acc += Ws[r][t] * x[t];
-            M[(long long)(j + r) * F.ld + col] = acc;
-        }
+    for (int i = threadIdx.x; i < NB_INNER * NB_INNER; i += 256) Wd[(i >> 5) * WD_LD + (i & 31)] = W[i];
+    for (int i = threadIdx.x; i < NB_INNER * RP_CW; i += 256) {
+        const int r = i / RP_CW, cc = i % RP_CW;
+        const int col = je + cs + cc;
+        const bool live = cs + cc < ncols && r < nbp && owned_col(ko, col, F.f);
+        xs[r * (RP_CW + 4) + cc] = live ? M[(long long)(j + r) * F.ld + col] : 0.0;
     }
+    __syncthreads();
+    if (ko.own_G > 1) {
+        // multi-GPU dense path: only owned columns are rewritten (ownership is uniform over a slab's 8-column groups
+        // except at block edges, so fall back to a guarded scalar write-back)
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+        double acc[4][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) acc[mi][0] = acc[mi][1] = 0.0;
+#pragma unroll
+        for (int k4 = 0; k4 < NB_INNER / 4; ++k4) {
+            const double b = xs[(k4 * 4 + t4) * (RP_CW + 4) + warp * 8 + g];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) dmma884(acc[mi][0], acc[mi][1], Wd[(mi * 8 + g) * WD_LD + k4 * 4 + t4], b);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const int r = mi * 8 + g;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = je + cs + warp * 8 + 2 * t4 + e;
+                if (r < nbp && col <= F.f && owned_col(ko, col, F.f)) M[(long long)(j + r) * F.ld + col] = acc[mi][e];
+            }
+        }
+        return;
+    }
+    rowpanel_slab_mma<RP_CW, 8>(Wd, xs, M + (long long)j * F.ld + je + cs, F.ld, nbp, min(RP_CW, ncols - cs),
+                                threadIdx.x >> 5, threadIdx.x & 31);
 }
 
 void launch_rowpanel(const LaunchCtx &c, const int *ids, int nfb, int j, int max_cols) {
-    dim3 grid((max_cols + 127) / 128, nfb, c.nbatch);
+    dim3 grid((max_cols + RP_CW - 1) / RP_CW, nfb, c.nbatch);
     if (grid.x == 0) grid.x = 1;
-    rowpanel_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.maxfb, c.ko);
+    launch_chain(rowpanel_kernel, grid, dim3(256), 0, c.stream, c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.maxfb, c.ko,
+                 c.f0 ? *c.f0 : DFront{}, c.f0 ? 1 : 0);
 }
 
 // =====================================================================================================
@@ -440,10 +520,12 @@ constexpr int TM = 128, TN = 64, TK = 16, TSTG = 3;
 constexpr int AS_LD = TK + 4, BS_LD = TN + 4;
 constexpr int TSTAGE_DOUBLES = TM * AS_LD + TK * BS_LD;
 
-__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
+#ifdef NGT_PANEL_CLOCKS
+__device__ long long g_upd_clk[8];
+#define NGT_UCLK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_upd_clk[i] = clock64(); } while (0)
+#else
+#define NGT_UCLK(i) do { } while (0)
+#endif
 __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     const int bytes = valid ? 8 : 0;   // 0 -> zero fill
@@ -453,10 +535,23 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+__device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 16 : 0;   // 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+
+// TMt = 128: the throughput tile.  TMt = 64: same kernel with half-height tiles (8 warps as 2 x 4, warp tile 32 x 16)
+// for launches that would otherwise leave most SMs idle -- the thin (K = 32) updates at the top of the assembly tree
+// are bound by each SM's L2 port (C tile in + out), so more, smaller CTAs finish sooner.
+template <int TMt>
 __global__ void __launch_bounds__(256, 2)
 update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode_in,
-                   int split, KOpt ko) {
-    const DFront F = fronts[ids[blockIdx.y]];
+                   int split, KOpt ko, DFront F0, int has_f0) {
+    constexpr int WM = TMt / 32, WN = 8 / WM, NI = TN / (8 * WN);
+    pdl_enter();
+    NGT_UCLK(0);
+    const DFront F = fetch_front(fronts, ids, blockIdx.y, F0, has_f0);
     Region R;
     int mode = mode_in, tile = blockIdx.x;
     if (mode_in == MODE_AB) {
@@ -466,58 +561,87 @@ update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, co
     }
     if (!get_region(F.f, F.fr, F.k, j, mode, R)) return;
     const int tiles_c = (R.c1 - R.c0 + TN - 1) / TN;
-    const int tiles_r = (R.r1 - R.r0 + TM - 1) / TM;
+    const int tiles_r = (R.r1 - R.r0 + TMt - 1) / TMt;
     const int tr = tile / tiles_c, tc = tile % tiles_c;
     if (tr >= tiles_r) return;
     double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
     const double *MA = F.a_ld ? pool + (long long)blockIdx.z * pool_stride + F.a_off : M;
     const long long lda = F.a_ld ? F.a_ld : F.ld;
-    const int rb = R.r0 + tr * TM, cb = R.c0 + tc * TN;
+    const int rb = R.r0 + tr * TMt, cb = R.c0 + tc * TN;
     const long long ld = F.ld;
     if (ko.own_G > 1 && !owned_col(ko, cb, F.f) && !owned_col(ko, min(cb + TN, R.c1) - 1, F.f)) return;
 
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wm = warp & 3, wn = warp >> 2;
+    const int wm = warp % WM, wn = warp / WM;
     const int g = lane >> 2, t4 = lane & 3;
 
-    // accumulators = C tile (issued first: their latency hides behind the pipeline prologue)
-    double acc[4][4][2];
+    // accumulators = C tile (issued first: their latency hides behind the pipeline prologue); 16-byte accesses when
+    // the tile starts on an even column (rows are 64-byte aligned) and every column is owned
+    const bool vec_c = ((cb & 1) == 0) && ko.own_G <= 1;
+    double acc[4][NI][2];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
         const int r = rb + wm * 32 + mi * 8 + g;
         const double *row = M + (long long)r * ld;
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
-            acc[mi][ni][0] = (r < R.r1 && c0 < R.c1) ? row[c0] : 0.0;
-            acc[mi][ni][1] = (r < R.r1 && c0 + 1 < R.c1) ? row[c0 + 1] : 0.0;
+        for (int ni = 0; ni < NI; ++ni) {
+            const int c0 = cb + wn * (8 * NI) + ni * 8 + 2 * t4;
+            if (vec_c && r < R.r1 && c0 + 1 < R.c1) {
+                const double2 v = *reinterpret_cast<const double2 *>(row + c0);
+                acc[mi][ni][0] = v.x;
+                acc[mi][ni][1] = v.y;
+            } else {
+                acc[mi][ni][0] = (r < R.r1 && c0 < R.c1) ? row[c0] : 0.0;
+                acc[mi][ni][1] = (r < R.r1 && c0 + 1 < R.c1) ? row[c0 + 1] : 0.0;
+            }
         }
     }
 
+    NGT_UCLK(1);
     const int nk = (R.k1 - R.k0 + TK - 1) / TK;
-    // per-thread load slots: A element (row ar + 16 i, pivot kb + ak), B element (pivot kb + bk + 4 i, column bc)
+    // Operand staging.  Interior tiles on even columns with an even pivot count move 16 bytes per cp.async:
+    //   A chunk (row ar2 + 32 i, pivots kb + ak2 .. +1), B chunk (pivot kb + bk2 + 8 i, columns bc2 .. +1);
+    // everything else moves single doubles: A element (row ar + 16 i, pivot kb + ak), B element (pivot kb + bk + 4 i,
+    // column bc).  Out-of-range slots are zero-filled either way.
+    const bool vec_ab = ((cb & 1) == 0) && (cb + TN <= R.c1) && (((R.k1 - R.k0) & 1) == 0) && F.a_ld == 0;
     const int ar = threadIdx.x >> 4, ak = threadIdx.x & 15;
     const int bk = threadIdx.x >> 6, bc = threadIdx.x & 63;
-    const double *pa = MA + (long long)(rb + ar) * lda + ak;
-    const double *pb = M + (long long)bk * ld + cb + bc;
+    const int ar2 = threadIdx.x >> 3, ak2 = (threadIdx.x & 7) * 2;
+    const int bk2 = threadIdx.x >> 5, bc2 = (threadIdx.x & 31) * 2;
+    const double *pa = vec_ab ? MA + (long long)(rb + ar2) * lda + ak2 : MA + (long long)(rb + ar) * lda + ak;
+    const double *pb = vec_ab ? M + (long long)bk2 * ld + cb + bc2 : M + (long long)bk * ld + cb + bc;
     unsigned amask = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) amask |= (rb + ar + 16 * i < R.r1) ? (1u << i) : 0u;
+    for (int i = 0; i < TMt / 16; ++i) amask |= (rb + (vec_ab ? ar2 + 32 * i : ar + 16 * i) < R.r1) ? (1u << i) : 0u;
     const bool bcol_ok = cb + bc < R.c1;
-    double *sa = smem + ar * AS_LD + ak;
-    double *sb = smem + TM * AS_LD + bk * BS_LD + bc;
+    double *sa = vec_ab ? smem + ar2 * AS_LD + ak2 : smem + ar * AS_LD + ak;
+    double *sb = vec_ab ? smem + TM * AS_LD + bk2 * BS_LD + bc2 : smem + TM * AS_LD + bk * BS_LD + bc;
     auto load_stage = [&](int stg, int kb) {
-        const bool ka = kb + ak < R.k1;
+        if (vec_ab) {
+            const bool ka = kb + ak2 < R.k1;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const bool ok = ka && ((amask >> i) & 1u);
-            cp_async8(sa + stg * TSTAGE_DOUBLES + i * 16 * AS_LD, ok ? pa + (long long)i * 16 * lda + kb : M, ok);
-        }
+            for (int i = 0; i < TMt / 32; ++i) {
+                const bool ok = ka && ((amask >> i) & 1u);
+                cp_async16(sa + stg * TSTAGE_DOUBLES + i * 32 * AS_LD, ok ? pa + (long long)i * 32 * lda + kb : M, ok);
+            }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool ok = bcol_ok && (kb + bk + 4 * i < R.k1);
-            cp_async8(sb + stg * TSTAGE_DOUBLES + i * 4 * BS_LD, ok ? pb + (long long)(kb + 4 * i) * ld : M, ok);
+            for (int i = 0; i < 2; ++i) {
+                const bool ok = kb + bk2 + 8 * i < R.k1;
+                cp_async16(sb + stg * TSTAGE_DOUBLES + i * 8 * BS_LD, ok ? pb + (long long)(kb + 8 * i) * ld : M, ok);
+            }
+        } else {
+            const bool ka = kb + ak < R.k1;
+#pragma unroll
+            for (int i = 0; i < TMt / 16; ++i) {
+                const bool ok = ka && ((amask >> i) & 1u);
+                cp_async8(sa + stg * TSTAGE_DOUBLES + i * 16 * AS_LD, ok ? pa + (long long)i * 16 * lda + kb : M, ok);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool ok = bcol_ok && (kb + bk + 4 * i < R.k1);
+                cp_async8(sb + stg * TSTAGE_DOUBLES + i * 4 * BS_LD, ok ? pb + (long long)(kb + 4 * i) * ld : M, ok);
+            }
         }
     };
 #pragma unroll
@@ -525,9 +649,11 @@ update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, co
         if (st < nk) load_stage(st, R.k0 + st * TK);
         cp_async_commit();
     }
+    NGT_UCLK(2);
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<TSTG - 2>();
         __syncthreads();
+        if (kt == 0) NGT_UCLK(3);
         const int nxt = kt + TSTG - 1;
         if (nxt < nk) load_stage(nxt % TSTG, R.k0 + nxt * TK);
         cp_async_commit();
@@ -535,18 +661,19 @@ update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, co
         const double *Bs = As + TM * AS_LD;
 #pragma unroll
         for (int k4 = 0; k4 < TK / 4; ++k4) {
-            double a[4], b[4];
+            double a[4], b[NI];
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) a[mi] = As[(wm * 32 + mi * 8 + g) * AS_LD + k4 * 4 + t4];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(k4 * 4 + t4) * BS_LD + wn * 32 + ni * 8 + g];
+            for (int ni = 0; ni < NI; ++ni) b[ni] = Bs[(k4 * 4 + t4) * BS_LD + wn * (8 * NI) + ni * 8 + g];
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
         }
     }
     cp_async_wait<0>();
+    NGT_UCLK(4);
     // epilogue: thread holds C[g][2*t4 + {0,1}] of every 8 x 8 tile
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
@@ -554,12 +681,17 @@ update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, co
         if (r >= R.r1) continue;
         double *row = M + (long long)r * ld;
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
-            if (c0 < R.c1 && owned_col(ko, c0, F.f)) row[c0] = acc[mi][ni][0];
-            if (c0 + 1 < R.c1 && owned_col(ko, c0 + 1, F.f)) row[c0 + 1] = acc[mi][ni][1];
+        for (int ni = 0; ni < NI; ++ni) {
+            const int c0 = cb + wn * (8 * NI) + ni * 8 + 2 * t4;
+            if (vec_c && c0 + 1 < R.c1) {
+                *reinterpret_cast<double2 *>(row + c0) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            } else {
+                if (c0 < R.c1 && owned_col(ko, c0, F.f)) row[c0] = acc[mi][ni][0];
+                if (c0 + 1 < R.c1 && owned_col(ko, c0 + 1, F.f)) row[c0 + 1] = acc[mi][ni][1];
+            }
         }
     }
+    NGT_UCLK(5);
 }
 
 // =====================================================================================================
@@ -724,6 +856,7 @@ __global__ void __launch_bounds__(256, 2)
 update_dmma_tmap_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode_in,
                         int split, KOpt ko, const __grid_constant__ CUtensorMap tmA,
                         const __grid_constant__ CUtensorMap tmB) {
+    pdl_enter();
     const DFront F = fronts[ids[blockIdx.y]];
     Region R;
     int mode = mode_in, tile = blockIdx.x;
@@ -830,9 +963,8 @@ void launch_update_tmap(const LaunchCtx &c, const int *ids, int j, int mode, int
     if (max_tiles <= 0) return;
     dim3 grid(max_tiles, 1, c.nbatch);
     const size_t smem = (size_t)TMS * TM_STAGE_BYTES;
-    update_dmma_tmap_kernel<<<grid, 256, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, 0, c.ko,
-                                                                  *static_cast<const CUtensorMap *>(tmA),
-                                                                  *static_cast<const CUtensorMap *>(tmB));
+    launch_chain(update_dmma_tmap_kernel, grid, dim3(256), smem, c.stream, c.pool, c.pool_stride, c.fronts, ids, j, mode, 0,
+                 c.ko, *static_cast<const CUtensorMap *>(tmA), *static_cast<const CUtensorMap *>(tmB));
 }
 
 // =====================================================================================================
@@ -958,7 +1090,9 @@ int update_tile_n(int gemm_path) { return gemm_path == 1 ? FT : (gemm_path == 2 
 int update_tile_k() { return TK; }
 
 void init_kernel_attributes() {
-    cudaFuncSetAttribute(update_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(update_dmma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)((size_t)TSTG * TSTAGE_DOUBLES * sizeof(double)));
+    cudaFuncSetAttribute(update_dmma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)((size_t)TSTG * TSTAGE_DOUBLES * sizeof(double)));
     cudaFuncSetAttribute(update_dmma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)((size_t)TSTG * TSTAGE_DOUBLES * sizeof(double)));
@@ -985,7 +1119,12 @@ void launch_update(const LaunchCtx &c, const int *ids, int nfb, int j, int mode,
                                                                      c.ko);
     } else {
         const size_t smem = (size_t)TSTG * TSTAGE_DOUBLES * sizeof(double);
-        update_dmma_kernel<<<grid, 256, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split, c.ko);
+        if (c.tile_m == 64)
+            launch_chain(update_dmma_kernel<64>, grid, dim3(256), smem, c.stream, c.pool, c.pool_stride, c.fronts, ids, j, mode,
+                         split, c.ko, c.f0 ? *c.f0 : DFront{}, c.f0 ? 1 : 0);
+        else
+            launch_chain(update_dmma_kernel<128>, grid, dim3(256), smem, c.stream, c.pool, c.pool_stride, c.fronts, ids, j, mode,
+                         split, c.ko, c.f0 ? *c.f0 : DFront{}, c.f0 ? 1 : 0);
     }
 }
 
@@ -1082,6 +1221,7 @@ void launch_ingest_dense(double *pool, long long pool_stride, int nbatch, const 
 __global__ void __launch_bounds__(256)
 assemble_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, const long long *child_ptr,
                 const int *child_ids, const int *inv, const long long *inv_off) {
+    pdl_enter();
     const int pid = ids[blockIdx.y];
     const DFront P = fronts[pid];
     const int a = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -1114,7 +1254,8 @@ void launch_assemble(const LaunchCtx &c, const int *ids, int nparents, int max_f
                      const int *child_ids, const int *inv, const long long *inv_off) {
     if (nparents <= 0 || max_f <= 0) return;
     dim3 grid((max_f + 7) / 8, nparents, c.nbatch);
-    assemble_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, child_ptr, child_ids, inv, inv_off);
+    launch_chain(assemble_kernel, grid, dim3(256), 0, c.stream, c.pool, c.pool_stride, c.fronts, ids, child_ptr, child_ids, inv,
+                 inv_off);
 }
 
 // =====================================================================================================

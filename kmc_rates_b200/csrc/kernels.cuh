@@ -103,6 +103,8 @@ struct LaunchCtx {
     cudaStream_t stream;
     int gemm_path;            // 0 DMMA, 1 DFMA
     KOpt ko;                  // {0,0,0,FUSE_COLS} outside the multi-GPU dense path
+    int tile_m = 0;             // DMMA Schur update tile height: 0 / 128 = throughput tile, 64 = latency tile
+    const DFront *f0 = nullptr; // host copy of the front when the launch covers exactly one (passed by value), else null
 };
 
 // ids: device array of front ids in this batch (nfb of them).
