@@ -261,6 +261,7 @@ struct Engine {
         return (R.k1 - R.k0) % tk == 0 && R.k0 % tk == 0 && R.c0 % 2 == 0 && (R.k1 - R.k0) >= 4 * tk;
     }
     bool use_graph = std::getenv("NGT_B200_NO_GRAPH") == nullptr;
+    bool use_cluster = std::getenv("NGT_B200_NO_CLUSTER") == nullptr;
     bool capturing = false, last_step_graph = false;
     long long steps_done = 0;
     cudaGraphExec_t graph_exec = nullptr;
@@ -440,7 +441,7 @@ struct Engine {
 
         build_phase2_structure();
         d_wbuf.alloc((size_t)nbatch * maxfb * ngt::NB_INNER * ngt::NB_INNER);
-        maxchunks = std::max(1, (S.max_front + ngt::RS_CHUNK - 1) / ngt::RS_CHUNK);
+        maxchunks = std::max(ngt::PANEL_CLUSTER, (S.max_front + ngt::RS_CHUNK - 1) / ngt::RS_CHUNK);
         d_rsbuf.alloc((size_t)nbatch * maxfb * maxchunks * ngt::NB_INNER);
         d_om.alloc((size_t)nbatch * m);
         d_ftau.alloc((size_t)nbatch * m);
@@ -551,13 +552,17 @@ struct Engine {
             int max_cols = 0;   // columns right of the panel incl. the tau column, widest live front
             for (int i = 0; i < nfb; ++i)
                 if (b.k[i] > j) max_cols = std::max(max_cols, b.f[i] + 1 - std::min(j + ngt::NB_INNER, b.k[i]));
-            if (max_cols - 1 > ngt::RS_SPLIT) {
+            // a handful of fronts (top of the assembly tree): clusters of CTAs per front do the row sums, the panel and
+            // the row panel in one launch
+            cj.panel_cluster = use_cluster && !wslot_per_step && cj.ko.own_G <= 1 &&
+                               (long long)nfb * nbatch * ngt::PANEL_CLUSTER <= 148 && max_cols <= ngt::PANEL_CLUSTER_MAX_COLS;
+            if (!cj.panel_cluster && max_cols - 1 > ngt::RS_SPLIT) {
                 ngt::launch_rowsum(cj, ids, nfb, j, max_cols - 1);
                 st.n_launches++;
             }
             ngt::launch_panel(cj, ids, nfb, j);
             st.n_launches++;
-            if (max_cols > cj.ko.fuse_cols) {
+            if (!cj.panel_cluster && max_cols > cj.ko.fuse_cols) {
                 ngt::launch_rowpanel(cj, ids, nfb, j, max_cols);
                 st.n_launches++;
             }

@@ -23,6 +23,16 @@ __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// thread-block cluster helpers (raw PTX; every thread of the CTA must call cluster_sync_all convergently)
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 static bool use_pdl() {
     static const bool on = std::getenv("NGT_B200_NO_PDL") == nullptr;
     return on;
@@ -42,6 +52,32 @@ static void launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t s
         cfg.attrs = at;
         cfg.numAttrs = 1;
     }
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+// same, as thread-block clusters of `cluster_x` CTAs along x
+template <typename... KArgs, typename... Args>
+static void launch_chain_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                                 Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = cluster_x;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    ++na;
+    if (use_pdl()) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = na;
     cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
@@ -184,15 +220,22 @@ __device__ long long g_gj_clk[8];
 #define NGT_GJ_T(i) do { } while (0)
 #endif
 
-template <int NT>
+// CL > 1: the launch is made of thread-block clusters of CL CTAs per front (single fronts at the top of the assembly
+// tree, where the whole GPU waits on this chain): all CTAs sum one column chunk of the 32 panel rows each, CTA 0 runs
+// the Gauss-Jordan, then all CTAs share the slabs of the row panel -- the stand-alone row-sum and row-panel launches
+// disappear from the chain.  Hand-over between the CTAs goes through global memory (rsbuf, wbuf) ordered by
+// release/acquire cluster barriers.
+template <int NT, int CL>
 __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 4))
 panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j,
-             double *wbuf, const double *rsbuf, int maxfb, int maxchunks, int *errflag, KOpt ko, DFront F0, int has_f0) {
+             double *wbuf, double *rsbuf, int maxfb, int maxchunks, int *errflag, KOpt ko, DFront F0, int has_f0) {
     pdl_enter();
     constexpr int NW = NT / 32;              // warps
     constexpr int CW = 64;                   // row-panel columns per slab
-    const DFront F = fetch_front(fronts, ids, blockIdx.x, F0, has_f0);
-    if (j >= F.k) return;
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int slot = CL > 1 ? (int)blockIdx.x / CL : (int)blockIdx.x;
+    const DFront F = fetch_front(fronts, ids, slot, F0, has_f0);
+    if (j >= F.k) return;                    // uniform over a cluster
     double *M = pool + (long long)blockIdx.y * pool_stride + F.off;
     const int nbp = min(NB_INNER, F.k - j);
     const int je = j + nbp;
@@ -210,47 +253,65 @@ panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const in
 
     // row sums over everything to the right of the panel (tau column excluded) and the T block.  A warp owns rows
     // warp, warp + NW, ...; their loads are issued together so one round of memory latency covers all of them.
-    {
-        constexpr int RPW = NB_INNER / NW;
+    constexpr int RPW = NB_INNER / NW;
+    double *rs = rsbuf + (((long long)blockIdx.y * maxfb + slot) * maxchunks) * NB_INNER;
+    // sum of columns [ca, ce) of the warp's rows (fixed order: four strided partial sums, then the lanes)
+    auto chunk_sums = [&](int ca, int ce, double (&sum)[RPW]) {
         double s0[RPW], s1[RPW], s2[RPW], s3[RPW];
 #pragma unroll
         for (int i = 0; i < RPW; ++i) s0[i] = s1[i] = s2[i] = s3[i] = 0.0;
-        const bool wide = F.f - je > RS_SPLIT;
-        if (wide) {
-            const int nch = (F.f - je + RS_CHUNK - 1) / RS_CHUNK;
-            const double *rs = rsbuf + (((long long)blockIdx.y * maxfb + blockIdx.x) * maxchunks) * NB_INNER;
+        const double *base = M + (long long)j * F.ld;
+        int c = ca + lane;
+        for (; c + 96 < ce; c += 128) {
 #pragma unroll
             for (int i = 0; i < RPW; ++i) {
                 const int u = warp + i * NW;
-                if (u < nbp)
-                    for (int ch = lane; ch < nch; ch += 32) s0[i] += rs[ch * NB_INNER + u];
-            }
-        } else {
-            const double *base = M + (long long)j * F.ld;
-            int c = je + lane;
-            for (; c + 96 < F.f; c += 128) {
-#pragma unroll
-                for (int i = 0; i < RPW; ++i) {
-                    const int u = warp + i * NW;
-                    if (u < nbp) {
-                        const double *row = base + (long long)u * F.ld;
-                        s0[i] += row[c]; s1[i] += row[c + 32]; s2[i] += row[c + 64]; s3[i] += row[c + 96];
-                    }
-                }
-            }
-            for (; c < F.f; c += 32) {
-#pragma unroll
-                for (int i = 0; i < RPW; ++i) {
-                    const int u = warp + i * NW;
-                    if (u < nbp) s0[i] += base[(long long)u * F.ld + c];
+                if (u < nbp) {
+                    const double *row = base + (long long)u * F.ld;
+                    s0[i] += row[c]; s1[i] += row[c + 32]; s2[i] += row[c + 64]; s3[i] += row[c + 96];
                 }
             }
         }
+        for (; c < ce; c += 32) {
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) {
+                const int u = warp + i * NW;
+                if (u < nbp) s0[i] += base[(long long)u * F.ld + c];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) sum[i] = warp_sum((s0[i] + s1[i]) + (s2[i] + s3[i]));
+    };
+    // sum of `nch` partial sums per row left in rs by other CTAs (this cluster's, or rowsum_kernel's for wide fronts)
+    auto partial_sums = [&](int nch, double (&sum)[RPW]) {
 #pragma unroll
         for (int i = 0; i < RPW; ++i) {
             const int u = warp + i * NW;
-            double sum = wide ? warp_sum(s0[i]) : warp_sum((s0[i] + s1[i]) + (s2[i] + s3[i]));
-            if (u >= nbp) sum = 1.0;   // padding rows behave like isolated absorbing nodes
+            double a = 0.0;
+            if (u < nbp)
+                for (int ch = lane; ch < nch; ch += 32) a += __ldcg(rs + ch * NB_INNER + u);
+            sum[i] = warp_sum(a);
+        }
+    };
+    double rowsum[RPW];
+    if (CL > 1) {
+        const int cw = (((F.f - je + CL - 1) / CL) + 31) & ~31;
+        const int ca = min(je + crank * cw, F.f);
+        chunk_sums(ca, min(ca + cw, F.f), rowsum);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) rs[crank * NB_INNER + warp + i * NW] = rowsum[i];
+        }
+        cluster_sync_all();
+    }
+    if (crank == 0) {
+        if (CL > 1) partial_sums(CL, rowsum);
+        else if (F.f - je > RS_SPLIT) partial_sums((F.f - je + RS_CHUNK - 1) / RS_CHUNK, rowsum);
+        else chunk_sums(je, F.f, rowsum);
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+            const int u = warp + i * NW;
+            const double sum = (u < nbp) ? rowsum[i] : 1.0;   // padding rows behave like isolated absorbing nodes
             const double t = (u < nbp && lane < nbp && lane != u) ? M[(long long)(j + u) * F.ld + j + lane] : 0.0;
             Xs[u][lane] = t;
             if (lane == 0) Ss[u] = sum;
@@ -263,7 +324,7 @@ panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const in
     __syncthreads();
     NGT_CLK(1);
 
-    if (warp < GJ_WARPS) {
+    if (crank == 0 && warp < GJ_WARPS) {
         const int c0 = warp * GJ_COLS;
         double X[GJ_COLS];
 #pragma unroll
@@ -340,17 +401,22 @@ panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const in
     }
     __syncthreads();
     NGT_CLK(3);
-    {
-        double *Wout = wbuf + ((long long)blockIdx.y * maxfb + blockIdx.x + ko.wslot) * (NB_INNER * NB_INNER);
+    double *Wout = wbuf + ((long long)blockIdx.y * maxfb + slot + ko.wslot) * (NB_INNER * NB_INNER);
+    if (crank == 0)
         for (int i = threadIdx.x; i < NB_INNER * NB_INNER; i += NT) Wout[i] = Xs[i >> 5][i & 31];
-    }
+    if (CL > 1) cluster_sync_all();
 
-    // fused row panel for narrow fronts: columns je..f (f = tau column) in slabs of CW staged through smem
+    // fused row panel (narrow fronts; always in the cluster variant): columns je..f (f = tau column) in slabs of CW
+    // staged through smem; the CTAs of a cluster take the slabs round-robin
     const int ncols = F.f + 1 - je;
     NGT_CLK(4);
-    if (ncols > ko.fuse_cols) return;
-    for (int i = threadIdx.x; i < NB_INNER * NB_INNER; i += NT) Wd[(i >> 5) * WD_LD + (i & 31)] = Xs[i >> 5][i & 31];
-    for (int cs = 0; cs < ncols; cs += CW) {
+    if (CL == 1 && ncols > ko.fuse_cols) return;
+    if (crank == 0) {
+        for (int i = threadIdx.x; i < NB_INNER * NB_INNER; i += NT) Wd[(i >> 5) * WD_LD + (i & 31)] = Xs[i >> 5][i & 31];
+    } else {
+        for (int i = threadIdx.x; i < NB_INNER * NB_INNER; i += NT) Wd[(i >> 5) * WD_LD + (i & 31)] = __ldcg(Wout + i);
+    }
+    for (int cs = crank * CW; cs < ncols; cs += CL * CW) {
         __syncthreads();
         for (int i = threadIdx.x; i < NB_INNER * CW; i += NT) {
             const int r = i / CW, cc = i % CW;
@@ -364,12 +430,17 @@ panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const in
 
 void launch_panel(const LaunchCtx &c, const int *ids, int nfb, int j) {
     dim3 grid(nfb, c.nbatch);
-    if ((long long)nfb * c.nbatch >= 2 * 148)   // many panels: favour occupancy over single-panel latency
-        launch_chain(panel_kernel<128>, grid, dim3(128), 0, c.stream, c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.rsbuf,
-                     c.maxfb, c.maxchunks, c.errflag, c.ko, c.f0 ? *c.f0 : DFront{}, c.f0 ? 1 : 0);
+    if (c.panel_cluster) {       // few fronts: a cluster of CTAs per front also does the row sums and the row panel
+        grid.x = nfb * PANEL_CLUSTER;
+        launch_chain_cluster(panel_kernel<512, PANEL_CLUSTER>, grid, dim3(512), 0, c.stream, PANEL_CLUSTER, c.pool, c.pool_stride,
+                             c.fronts, ids, j, c.wbuf, c.rsbuf, c.maxfb, c.maxchunks, c.errflag, c.ko,
+                             c.f0 ? *c.f0 : DFront{}, c.f0 ? 1 : 0);
+    } else if ((long long)nfb * c.nbatch >= 2 * 148)   // many panels: favour occupancy over single-panel latency
+        launch_chain(panel_kernel<128, 1>, grid, dim3(128), 0, c.stream, c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf,
+                     c.rsbuf, c.maxfb, c.maxchunks, c.errflag, c.ko, c.f0 ? *c.f0 : DFront{}, c.f0 ? 1 : 0);
     else
-        launch_chain(panel_kernel<512>, grid, dim3(512), 0, c.stream, c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf, c.rsbuf,
-                     c.maxfb, c.maxchunks, c.errflag, c.ko, c.f0 ? *c.f0 : DFront{}, c.f0 ? 1 : 0);
+        launch_chain(panel_kernel<512, 1>, grid, dim3(512), 0, c.stream, c.pool, c.pool_stride, c.fronts, ids, j, c.wbuf,
+                     c.rsbuf, c.maxfb, c.maxchunks, c.errflag, c.ko, c.f0 ? *c.f0 : DFront{}, c.f0 ? 1 : 0);
 }
 
 // =====================================================================================================

@@ -47,6 +47,8 @@ struct KOpt {
     int fuse_cols;   // row-panel fusion threshold (FUSE_COLS; 0 forces the stand-alone row-panel kernel)
 };
 
+constexpr int PANEL_CLUSTER = 8; // CTAs per front in the cluster variant of the panel kernel
+constexpr int PANEL_CLUSTER_MAX_COLS = 2048;   // widest row panel the cluster variant takes on
 constexpr int RS_CHUNK = 512;   // columns per partial-row-sum CTA (one warp per panel row)
 constexpr int RS_SPLIT = 4096;  // fronts with more columns right of the panel get multi-CTA row sums
 constexpr int FUSE_COLS = NGT_FUSE_COLS; // fronts with at most this many columns apply W to their row panel inside the panel kernel
@@ -103,6 +105,8 @@ struct LaunchCtx {
     cudaStream_t stream;
     int gemm_path;            // 0 DMMA, 1 DFMA
     KOpt ko;                  // {0,0,0,FUSE_COLS} outside the multi-GPU dense path
+    int panel_cluster = 0;      // 1: panel kernel runs as clusters of PANEL_CLUSTER CTAs per front and includes the row
+                                // sums and the row panel (no rowsum / rowpanel launch for this step)
     int tile_m = 0;             // DMMA Schur update tile height: 0 / 128 = throughput tile, 64 = latency tile
     const DFront *f0 = nullptr; // host copy of the front when the launch covers exactly one (passed by value), else null
 };

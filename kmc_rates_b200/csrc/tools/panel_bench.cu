@@ -93,6 +93,21 @@ int main(int argc, char **argv) {
             timeit("update AB (j=0), 64-row tiles", [&] { ngt::launch_update(c64, ids, 1, 0, ngt::MODE_AB, ta2 + tb2, ta2); });
         }
         timeit("empty-ish kernel (rowsum early exit)", [&] { ngt::launch_rowsum(c, ids, 1, 0, 512); });
+        {
+            ngt::LaunchCtx cc = c;
+            cc.panel_cluster = 1;
+            timeit("panel, cluster variant (row sums + GJ + row panel)", [&] { ngt::launch_panel(cc, ids, 1, 0); });
+            ngt::get_region(f, 0, k, 0, ngt::MODE_A, R);
+            const int ta2 = ((R.r1 - R.r0 + 63) / 64) * ((R.c1 - R.c0 + 63) / 64);
+            ngt::get_region(f, 0, k, 0, ngt::MODE_B, R);
+            const int tb2 = ((R.r1 - R.r0 + 63) / 64) * ((R.c1 - R.c0 + 63) / 64);
+            ngt::LaunchCtx c64 = c;
+            c64.tile_m = 64;
+            timeit("cluster panel + AB(64-row) chain", [&] {
+                ngt::launch_panel(cc, ids, 1, 0);
+                ngt::launch_update(c64, ids, 1, 0, ngt::MODE_AB, ta2 + tb2, ta2);
+            });
+        }
         timeit("panel+rowpanel+AB chain", [&] {
             ngt::launch_panel(c, ids, 1, 0);
             ngt::launch_rowpanel(c, ids, 1, 0, f + 1 - 32);
