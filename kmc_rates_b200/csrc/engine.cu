@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -1089,6 +1090,75 @@ Engine *make_engine(const ngt_options *opt, int64_t nbatch) {
     return E;
 }
 
+// Host buffers of the sparse analysis, kept between calls (one set per process, handed to one build at a time): on a
+// fresh allocation the first-touch page faults of these ~150 MB cost more than the passes that fill them.
+struct HostWorkspace {
+    ngt::EdgeIndex ix;
+    ngt::Adjacency g;
+    ngt::IndexScratch is;
+    std::vector<int> row_node, korig;
+    std::vector<long long> row_ptr, tau_dest, dest;
+    std::vector<std::vector<int32_t> > marks;
+    std::vector<int32_t> row_cnt;
+    std::vector<char> reach;
+    std::vector<int32_t> stack;
+    size_t bytes() const {
+        size_t b = ix.outptr.capacity() * 8 + ix.ent.capacity() * 4 + ix.present.capacity() + g.ptr.capacity() * 8 +
+                   g.adj.capacity() * 4 + is.tmp.capacity() * 4 + (is.aptr.capacity() + is.ucnt.capacity()) * 8 +
+                   row_node.capacity() * 4 + korig.capacity() * 4 + (row_ptr.capacity() + tau_dest.capacity() + dest.capacity()) * 8;
+        for (auto &v : is.c_out) b += v.capacity() * 4;
+        for (auto &v : is.c_adj) b += v.capacity() * 4;
+        for (auto &v : is.seen) b += v.capacity() * 4;
+        for (auto &v : is.w_out) b += v.capacity() * 8;
+        for (auto &v : is.w_adj) b += v.capacity() * 8;
+        for (auto &v : marks) b += v.capacity() * 4;
+        return b;
+    }
+};
+// a piece of work that runs beside the symbolic analysis; its exception (if any) is re-thrown where the work used to be
+struct SideTask {
+    std::thread th;
+    std::exception_ptr err;
+    template <class F>
+    void start(F f) {
+        th = std::thread([this, f] {
+            try { f(); } catch (...) { err = std::current_exception(); }
+        });
+    }
+    void finish() {
+        if (th.joinable()) th.join();
+        if (err) {
+            std::exception_ptr e = err;
+            err = nullptr;
+            std::rethrow_exception(e);
+        }
+    }
+    ~SideTask() { if (th.joinable()) th.join(); }
+};
+
+static std::mutex g_ws_mu;
+static std::unique_ptr<HostWorkspace> g_ws_cached;
+constexpr size_t HOST_WS_KEEP_BYTES = (size_t)1 << 30;   // larger workspaces are released after use
+
+struct WorkspaceLease {
+    std::unique_ptr<HostWorkspace> ws;
+    WorkspaceLease() {
+        std::lock_guard<std::mutex> lk(g_ws_mu);
+        ws = std::move(g_ws_cached);
+        if (!ws) ws.reset(new HostWorkspace());
+    }
+    ~WorkspaceLease() {
+        if (ws && ws->bytes() <= HOST_WS_KEEP_BYTES) {
+            std::lock_guard<std::mutex> lk(g_ws_mu);
+            if (!g_ws_cached) g_ws_cached = std::move(ws);
+        }
+    }
+};
+void trim_host_workspace() {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    g_ws_cached.reset();
+}
+
 void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, const double *k,
                   int64_t nA, const int64_t *A, int64_t nB, const int64_t *B) {
     auto t0 = std::chrono::steady_clock::now();
@@ -1101,9 +1171,11 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
     E->A.assign(A, A + nA);
     E->B.assign(B, B + nB);
     E->validate_groups();
-    ngt::EdgeIndex ix;
-    ngt::Adjacency g;
-    ngt::index_edges(n, nnz, src, dst, ix, g);
+    WorkspaceLease lease;
+    HostWorkspace &W = *lease.ws;
+    ngt::EdgeIndex &ix = W.ix;
+    ngt::Adjacency &g = W.g;
+    ngt::index_edges(n, nnz, src, dst, ix, g, &W.is);
     if (ix.range_error) throw InvalidError("rate endpoint out of range");
     std::vector<char> &present = ix.present;
     std::vector<int64_t> &outdeg = ix.outptr;     // row pointers of the CSR-by-source entry lists
@@ -1112,11 +1184,56 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
     for (int64_t u = 0; u < n; ++u)
         if (present[u] && outdeg[u + 1] == outdeg[u]) throw InvalidError("node " + std::to_string(u) + " has no outgoing rate");
     tm.lap("index edges (validate, CSR buckets, adjacency)");
+    // Beside the analysis (which leaves cores idle while it walks the top of the dissection tree): (1) the device is
+    // initialised and the rate constants are uploaded, (2) the entries that survive de-duplication are counted per
+    // source node ("last wins", std::map semantics of ngt.pyx:76-81) for the rate -> slot table built afterwards.
+    const std::vector<int32_t> &ent = ix.ent;
+    auto dedup_row = [&](int64_t u, std::vector<int32_t> &mark, auto &&emit) {
+        // later duplicates win: walk the row backwards and keep the first sighting of every destination
+        for (int64_t q = outdeg[u + 1]; q-- > outdeg[u];) {
+            const int32_t e = ent[q];
+            const int64_t v = dst[e];
+            if (mark[v] == (int32_t)u) continue;
+            mark[v] = (int32_t)u;
+            emit(e);
+        }
+    };
+    SideTask device_task, count_task;
+    device_task.start([&] {
+        E->init_device();
+        E->d_k.alloc((size_t)nnz * E->nbatch);
+        if (k) {
+            CK(cudaMemcpy(E->d_k.p, k, (size_t)nnz * E->nbatch * sizeof(double), cudaMemcpyHostToDevice));
+            E->values_loaded = true;
+        }
+    });
+    std::vector<int32_t> &row_cnt = W.row_cnt;
+    row_cnt.assign(n, 0);
+    count_task.start([&] {
+        const int nthr = n < 4096 ? 1 : 4;
+        if ((int)W.marks.size() < nthr) W.marks.resize(nthr);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthr; ++t)
+            th.emplace_back([&, t] {
+                std::vector<int32_t> &mark = W.marks[t];
+                mark.assign(n, -1);
+                for (int64_t u = n * t / nthr; u < n * (t + 1) / nthr; ++u) {
+                    int32_t c = 0;
+                    dedup_row(u, mark, [&](int32_t) { ++c; });
+                    row_cnt[u] = c;
+                }
+            });
+        for (auto &x : th) x.join();
+    });
     // Nodes with no (undirected) path to A ∪ B cannot influence any result; like the reference's Python front end
-    // (_kmc_rates.py:414-425) they are dropped before elimination.  Their committors read NaN.
-    {
-        std::vector<int32_t> stack;
-        std::vector<char> reach(n, 0);
+    // (_kmc_rates.py:414-425) they are dropped before elimination.  Their committors read NaN.  Almost every network
+    // is connected, so the reachability sweep runs on its own thread beside the analysis, which is only repeated on
+    // the pruned node set when the sweep did find something to drop.
+    std::vector<char> &reach = W.reach;
+    reach.assign(n, 0);
+    std::thread sweep([&] {
+        std::vector<int32_t> &stack = W.stack;
+        stack.clear();
         for (int64_t a : E->A) if (!reach[a]) { reach[a] = 1; stack.push_back((int32_t)a); }
         for (int64_t b : E->B) if (!reach[b]) { reach[b] = 1; stack.push_back((int32_t)b); }
         while (!stack.empty()) {
@@ -1127,58 +1244,56 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
                 if (!reach[v]) { reach[v] = 1; stack.push_back(v); }
             }
         }
-        for (int64_t u = 0; u < n; ++u) if (!reach[u]) present[u] = 0;
+    });
+    try {
+        ngt::analyse_sparse(g, present, E->A, E->B, E->opt.leaf_size, E->S);
+    } catch (...) {
+        sweep.join();
+        throw;
     }
-    tm.lap("prune unreachable");
-    ngt::analyse_sparse(g, present, E->A, E->B, E->opt.leaf_size, E->S);
+    sweep.join();
+    {
+        bool pruned = false;
+        for (int64_t u = 0; u < n; ++u)
+            if (present[u] && !reach[u]) { present[u] = 0; pruned = true; }
+        tm.lap("analysis (reachability sweep alongside)");
+        if (pruned) {
+            E->S = Symbolic();
+            ngt::analyse_sparse(g, present, E->A, E->B, E->opt.leaf_size, E->S);
+            tm.lap("analysis repeated on the pruned node set");
+        }
+    }
     const Symbolic &S = E->S;
-    tm.lap("analyse_sparse total");
 
-    // CSR by source over present nodes, (src,dst) duplicates resolved "last wins" (std::map semantics, ngt.pyx:76-81)
-    const std::vector<int32_t> &ent = ix.ent;
-    // rows = present nodes in id order; each worker thread handles a contiguous slice of rows twice:
-    // pass 1 counts the entries that survive de-duplication, pass 2 writes source indices and slots.
-    std::vector<int> row_node;
+    // CSR by source over present nodes, (src,dst) duplicates resolved "last wins"; rows = present nodes in id order,
+    // each worker thread writes the source indices and slots of a contiguous slice of rows
+    count_task.finish();
+    std::vector<int> &row_node = W.row_node;
+    row_node.clear();
     for (int64_t u = 0; u < n; ++u)
         if (present[u]) row_node.push_back((int)u);
     const int64_t nrows = (int64_t)row_node.size();
-    std::vector<long long> row_ptr(nrows + 1, 0), tau_dest(nrows);
-    std::vector<int> korig;
-    std::vector<long long> dest;
+    std::vector<long long> &row_ptr = W.row_ptr, &tau_dest = W.tau_dest, &dest = W.dest;
+    std::vector<int> &korig = W.korig;
+    row_ptr.assign(nrows + 1, 0);
+    tau_dest.resize(nrows);
     {
         unsigned hw = std::thread::hardware_concurrency();
         int nthr = (int)std::max(1u, std::min(hw ? hw : 1u, 32u));
         if (nrows < 4096) nthr = 1;
-        std::vector<std::vector<int32_t> > marks(nthr);
-        auto dedup_row = [&](int64_t u, std::vector<int32_t> &mark, auto &&emit) {
-            // later duplicates win: walk the row backwards and keep the first sighting of every destination
-            for (int64_t q = outdeg[u + 1]; q-- > outdeg[u];) {
-                const int32_t e = ent[q];
-                const int64_t v = dst[e];
-                if (mark[v] == (int32_t)u) continue;
-                mark[v] = (int32_t)u;
-                emit(e);
-            }
-        };
+        std::vector<std::vector<int32_t> > &marks = W.marks;
+        if ((int)marks.size() < nthr) marks.resize(nthr);
         auto run = [&](auto &&body) {
             std::vector<std::thread> th;
             for (int t = 0; t < nthr; ++t) th.emplace_back([&, t] { body(t, nrows * t / nthr, nrows * (t + 1) / nthr); });
             for (auto &x : th) x.join();
         };
-        run([&](int t, int64_t r0, int64_t r1) {
-            marks[t].assign(n, -1);
-            for (int64_t r = r0; r < r1; ++r) {
-                long long c = 0;
-                dedup_row(row_node[r], marks[t], [&](int32_t) { ++c; });
-                row_ptr[r + 1] = c;
-            }
-        });
-        for (int64_t r = 0; r < nrows; ++r) row_ptr[r + 1] += row_ptr[r];
+        for (int64_t r = 0; r < nrows; ++r) row_ptr[r + 1] = row_ptr[r] + row_cnt[row_node[r]];
         korig.resize(row_ptr[nrows]);
         dest.resize(row_ptr[nrows]);
         std::vector<char> bad(nthr, 0);
         run([&](int t, int64_t r0, int64_t r1) {
-            std::fill(marks[t].begin(), marks[t].end(), -1);
+            marks[t].assign(n, -1);
             for (int64_t r = r0; r < r1; ++r) {
                 const int64_t u = row_node[r];
                 const int32_t pu = S.pos[u];
@@ -1203,8 +1318,9 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
     }
     E->n_rows = (int)row_node.size();
     tm.lap("CSR + slot table");
-    E->init_device();
-    tm.lap("init device");
+    device_task.finish();
+    CK(cudaSetDevice(E->device));
+    tm.lap("init device + upload rates (joined)");
     E->d_row_ptr.upload(row_ptr);
     E->d_row_node.upload(row_node);
     E->d_korig.upload(korig);
@@ -1213,12 +1329,6 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
     tm.lap("upload ingest tables");
     E->upload_structure();
     tm.lap("upload structure + alloc pools");
-    E->d_k.alloc((size_t)nnz * E->nbatch);
-    if (k) {
-        CK(cudaMemcpy(E->d_k.p, k, (size_t)nnz * E->nbatch * sizeof(double), cudaMemcpyHostToDevice));
-        E->values_loaded = true;
-    }
-    tm.lap("upload rates");
     E->st.ms_symbolic = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
@@ -1562,7 +1672,10 @@ int ngt_profile_schur(ngt_handle h, double *ms_schur, double *flops, int64_t *la
     });
 }
 
-void ngt_trim_device_cache(void) { g_cache.trim(); }
+void ngt_trim_device_cache(void) {
+    g_cache.trim();
+    trim_host_workspace();
+}
 
 int ngt_dist_begin(ngt_handle h, int32_t rank, int32_t world) {
     return guard([&] { eng(h)->dist_begin(rank, world); });

@@ -31,6 +31,9 @@ int main(int argc, char **argv) {
         ngt::Symbolic S;
         ngt::analyse_sparse(g, ix.present, A, B, 0, S);
         auto t2 = std::chrono::steady_clock::now();
+        unsigned long long hsh = 1469598103934665603ULL;   // FNV-1a over the elimination order
+        for (int32_t v : S.node_at) { hsh ^= (unsigned long long)(unsigned)v; hsh *= 1099511628211ULL; }
+        std::printf("rep %d: order hash %016llx\n", r, hsh);
         std::printf("rep %d: index %.2f ms  analyse %.2f ms  fronts %zu levels %d max_front %d pool %.3f GB flops %.3e launches~%zu batches\n",
                     r, std::chrono::duration<double, std::milli>(t1 - t0).count(),
                     std::chrono::duration<double, std::milli>(t2 - t1).count(), S.fronts.size(), S.n_levels, S.max_front,
