@@ -409,8 +409,8 @@ def main():
             "flops_per_step": pfl, "launches_per_step": pl, "kernel_ms_per_step": pms,
             "share_of_step": pms / step_ms_single,
             "share_note": "kernel CUDA-event time / duration of the same profiled (event-bracketed, graph-free) pass; "
-                          "ncu launch list of the same step: profiles/r01_launches_c2.md (panel_kernel, latency-bound "
-                          "32x32 Gauss-Jordan, is co-dominant there)",
+                          "ncu launch list of the same step: profiles/r01_launches_c2.md (panel_kernel, a 32-step "
+                          "Gauss-Jordan dependency chain per launch, is co-dominant there)",
             "hbm_model": {
                 "note": "SURVEY §8(d) sparse-phase model: bytes a one-node-at-a-time elimination would stream",
                 "alg_bytes_per_step": st["alg_bytes"], "achieved_GBs": st["alg_bytes"] / (ms_per_step * 1e-3) / 1e9,
