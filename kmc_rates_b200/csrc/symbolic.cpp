@@ -176,7 +176,11 @@ struct Sub {
 struct Dissector {
     int leaf;
     int max_par_depth;
-    double min_bal = 0.25;   // smaller side of a split should hold at least this fraction
+    // smaller side of a split should hold at least this fraction.  Balanced trees cost more flops but fewer dependent
+    // panel steps, and the GPU is latency-bound at the top of the tree: on the 10^5-minima landscape 0.25 / 0.30 /
+    // 0.35 / 0.40 give 1.08 / 1.11 / 1.19 / 1.29e10 flops, 5.2 / 5.15 / 4.76 / 4.91 ms per step and 48 / 45 / 38 / 37 ms
+    // of ordering time
+    double min_bal = 0.35;
     bool trace = std::getenv("NGT_B200_TIMING") != nullptr && std::getenv("NGT_B200_ND_TRACE") != nullptr;
 
     // result of dissecting one subset: nodes in elimination order + supernode sizes
