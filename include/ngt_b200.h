@@ -155,7 +155,8 @@ int ngt_dist_root(ngt_handle h, double **dptr, int64_t *ndoubles);
 int ngt_dist_finish(ngt_handle h);
 
 /* Device buffers of destroyed handles are cached per process for reuse by later handles (cudaMalloc/cudaFree of the
- * front pools cost ~0.1 s).  This returns the cached memory to the driver. */
+ * front pools cost ~0.1 s), and so are the host temporaries of the sparse analysis (up to 1 GB; their first-touch page
+ * faults cost more than the analysis passes that fill them).  This returns both to the driver / the allocator. */
 void ngt_trim_device_cache(void);
 
 const char *ngt_last_error(void);
