@@ -216,11 +216,17 @@ struct Dissector {
         visit.push_back(start);
         lvl[start] = 0;
         nlev = 1;
+        const int32_t *adj = G.adj.data();
+        const int32_t last = (int32_t)G.adj.size() - 1;
         while (head < visit.size()) {
             const int32_t u = visit[head++];
             const int32_t lu = lvl[u] + 1;
+            // the queue is known a few nodes ahead: pull the adjacency row of a later node and the level slots of
+            // this node's later neighbours towards the core (the sweep is a chain of dependent cache misses otherwise)
+            if (head + 4 < visit.size()) __builtin_prefetch(adj + G.ptr[visit[head + 4]]);
             for (int32_t e = G.ptr[u]; e < G.ptr[u + 1]; ++e) {
-                const int32_t v = G.adj[e];
+                __builtin_prefetch(&lvl[adj[std::min(e + 8, last)]]);
+                const int32_t v = adj[e];
                 if (lvl[v] >= 0) continue;
                 lvl[v] = lu;
                 nlev = lu + 1;
@@ -239,11 +245,15 @@ struct Dissector {
         for (int32_t v : members) cap += (size_t)(G.ptr[v + 1] - G.ptr[v]);
         H.adj.clear();
         H.adj.reserve(cap);
+        const int32_t *adj = G.adj.data();
+        const int32_t last = (int32_t)G.adj.size() - 1;
         for (int32_t i = 0; i < H.n; ++i) {
             const int32_t v = members[i];
             H.glob[i] = G.glob[v];
+            if (i + 4 < H.n) __builtin_prefetch(adj + G.ptr[members[i + 4]]);
             for (int32_t e = G.ptr[v]; e < G.ptr[v + 1]; ++e) {
-                const int32_t w = newid[G.adj[e]];
+                __builtin_prefetch(&newid[adj[std::min(e + 8, last)]]);
+                const int32_t w = newid[adj[e]];
                 if (w >= 0) H.adj.push_back(w);
             }
             H.ptr[i + 1] = (int32_t)H.adj.size();
@@ -628,6 +638,7 @@ void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
             }
         });
     }
+    tm.lap("  symbolic: own neighbours (parallel)");
     // phase B (in elimination order): add what the children pass up
     for (int32_t s = 0; s < ns; ++s) {
         const int32_t first = sn_start[s], last = sn_start[s + 1];
@@ -646,7 +657,7 @@ void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
         else F.parent = S.pos_front[U[0]];
         if (F.parent >= 0) kids[F.parent].push_back(s);
     }
-    tm.lap("supernodal symbolic");
+    tm.lap("  symbolic: merge children (serial)");
     // root
     {
         Front &R = S.fronts[ns];
@@ -671,6 +682,7 @@ void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
     }
     S.fronts[ns].idx_off = (int64_t)S.fidx.size();
     for (int64_t p = S.nI; p < npos; ++p) S.fidx.push_back((int32_t)p);
+    tm.lap("  symbolic: index lists");
     finish_layout(S);
     tm.lap("layout, maps, batches");
 }
