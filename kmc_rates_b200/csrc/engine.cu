@@ -173,8 +173,8 @@ struct Engine {
     DevBuf<DFront> d_fronts;
     std::vector<DFront> h_fronts, h_p2fronts;   // host mirrors (single-front launches pass the descriptor by value)
     DevBuf<int> d_ids;              // batch ids (phase 1), then extend-add rounds
-    DevBuf<int> d_inv, d_child_ids;
-    DevBuf<long long> d_inv_off, d_child_ptr;
+    DevBuf<int> d_row_child, d_row_crow, d_rel;                 // assembly: per-parent-row contribution lists, relative maps
+    DevBuf<long long> d_row_base, d_arow_ptr, d_rel_off;
     DevBuf<int> d_fidx;
     DevBuf<long long> d_idx_off;
     std::vector<HostBatch> batches;
@@ -273,6 +273,12 @@ struct Engine {
     cudaEvent_t sync_ev[2] = {nullptr, nullptr};
     cudaEvent_t sync_event(int i) { return sync_ev[i]; }
     bool profile_schur = false;
+    // which launches the profiled pass brackets with events: Schur updates (the roofline kernel) unless the
+    // experiment switch NGT_B200_PROFILE_KIND says "assemble" or "panel"
+    int profile_kind = [] {
+        const char *e = std::getenv("NGT_B200_PROFILE_KIND");
+        return !e ? 0 : (std::string(e) == "assemble" ? 1 : (std::string(e) == "panel" ? 2 : 0));
+    }();
     std::vector<cudaEvent_t> prof_ev;   // pairs around every update launch when profile_schur
     size_t prof_used = 0;
     cudaEvent_t prof_event() {
@@ -390,8 +396,8 @@ struct Engine {
         batches = make_batches(S, flat);
         for (auto &b : batches) maxfb = std::max(maxfb, (int)b.ids.size());
 
-        // assembly: per tree level the parents that have children (one launch per level), and for every child the
-        // inverse of its relative map (parent local index -> child update index)
+        // assembly: per tree level the parents that have children (one launch per level), and for every parent row the
+        // list of child rows that add into it
         rounds.clear();
         {
             std::vector<std::vector<int> > per_level(S.n_levels);
@@ -412,19 +418,47 @@ struct Engine {
                     rounds.push_back(rd);
                 }
             }
-            std::vector<long long> inv_off(nf + 1, 0);
-            for (int c = 0; c < nf; ++c)
-                inv_off[c + 1] = inv_off[c] + (S.fronts[c].parent >= 0 ? S.fronts[S.fronts[c].parent].f : 0);
-            std::vector<int> inv(inv_off[nf], -1);
-            for (int c = 0; c < nf; ++c) {
-                if (S.fronts[c].parent < 0) continue;
-                for (int jx = 0; jx < S.fronts[c].m; ++jx) inv[inv_off[c] + S.rel[S.rel_off[c] + jx]] = jx;
-            }
-            d_inv.upload(inv);
-            d_inv_off.upload(inv_off);
-            std::vector<long long> cp(S.child_ptr.begin(), S.child_ptr.end());
-            d_child_ptr.upload(cp);
-            d_child_ids.upload(S.child_ids);
+            // per parent row: the (child, child update row) pairs that contribute to it, children in their fixed order
+            std::vector<long long> row_base(nf + 1, 0);
+            for (int p = 0; p < nf; ++p) row_base[p + 1] = row_base[p] + (S.child_ptr[p + 1] > S.child_ptr[p] ? S.fronts[p].f : 0);
+            std::vector<long long> row_ptr(row_base[nf] + 1, 0);
+            // every parent owns a contiguous range of row_ptr, so parents are counted and filled independently
+            unsigned hw = std::thread::hardware_concurrency();
+            const int nthr = nf < 512 ? 1 : (int)std::max(1u, std::min(hw ? hw : 1u, 8u));
+            auto over_parents = [&](auto &&body) {
+                std::vector<std::thread> th;
+                for (int t = 1; t < nthr; ++t)
+                    th.emplace_back([&, t] { for (int p = nf * t / nthr; p < nf * (t + 1) / nthr; ++p) body(p); });
+                for (int p = 0; p < nf / nthr; ++p) body(p);
+                for (auto &x : th) x.join();
+            };
+            over_parents([&](int p) {
+                for (long long ci = S.child_ptr[p]; ci < S.child_ptr[p + 1]; ++ci) {
+                    const int c = S.child_ids[ci];
+                    for (int jx = 0; jx < S.fronts[c].m; ++jx) row_ptr[row_base[p] + S.rel[S.rel_off[c] + jx] + 1]++;
+                }
+            });
+            for (size_t i = 0; i + 1 < row_ptr.size(); ++i) row_ptr[i + 1] += row_ptr[i];
+            std::vector<int> row_child(row_ptr.back()), row_crow(row_ptr.back());
+            over_parents([&](int p) {
+                if (S.child_ptr[p + 1] == S.child_ptr[p]) return;
+                std::vector<long long> fill(row_ptr.begin() + row_base[p], row_ptr.begin() + row_base[p] + S.fronts[p].f);
+                for (long long ci = S.child_ptr[p]; ci < S.child_ptr[p + 1]; ++ci) {
+                    const int c = S.child_ids[ci];
+                    for (int jx = 0; jx < S.fronts[c].m; ++jx) {
+                        const long long w = fill[S.rel[S.rel_off[c] + jx]]++;
+                        row_child[w] = c;
+                        row_crow[w] = jx;
+                    }
+                }
+            });
+            d_row_base.upload(row_base);
+            d_arow_ptr.upload(row_ptr);
+            d_row_child.upload(row_child);
+            d_row_crow.upload(row_crow);
+            d_rel.upload(S.rel);
+            std::vector<long long> ro(S.rel_off.begin(), S.rel_off.end());
+            d_rel_off.upload(ro);
         }
         d_ids.upload(flat);
         d_fidx.upload(S.fidx);
@@ -557,6 +591,8 @@ struct Engine {
             // the row panel in one launch
             cj.panel_cluster = use_cluster && !wslot_per_step && cj.ko.own_G <= 1 &&
                                (long long)nfb * nbatch * ngt::PANEL_CLUSTER <= 148 && max_cols <= ngt::PANEL_CLUSTER_MAX_COLS;
+            const bool pe_panel = profile_schur && profile_kind == 2;
+            if (pe_panel) CK(cudaEventRecord(prof_event(), stream));
             if (!cj.panel_cluster && max_cols - 1 > ngt::RS_SPLIT) {
                 ngt::launch_rowsum(cj, ids, nfb, j, max_cols - 1);
                 st.n_launches++;
@@ -567,6 +603,7 @@ struct Engine {
                 ngt::launch_rowpanel(cj, ids, nfb, j, max_cols);
                 st.n_launches++;
             }
+            if (pe_panel) { CK(cudaEventRecord(prof_event(), stream)); st.reserved[0] += 1; }
             double fl = 0, dummy = 0;
             int ta = max_tiles(b, j, ngt::MODE_A, tm, tn, fl);
             int tb = max_tiles(b, j, ngt::MODE_B, tm, tn, fl);
@@ -615,11 +652,12 @@ struct Engine {
                 d2_async = use_lookahead && (long long)td2 * live * nbatch >= 148;
             }
             auto timed = [&](cudaStream_t sx, auto &&fn) {
-                if (profile_schur) CK(cudaEventRecord(prof_event(), sx));
+                const bool pe = profile_schur && profile_kind == 0;
+                if (pe) CK(cudaEventRecord(prof_event(), sx));
                 fn();
-                if (profile_schur) CK(cudaEventRecord(prof_event(), sx));
+                if (pe) CK(cudaEventRecord(prof_event(), sx));
                 st.n_launches++;
-                st.reserved[0] += 1;   // Schur-update launches
+                if (profile_kind == 0) st.reserved[0] += 1;   // Schur-update launches
             };
             if (ta + tb > 0) timed(stream, [&] { ngt::launch_update(c_ab, ids, nfb, j, ngt::MODE_AB, ta + tb, ta); });
             if (td1a + td1b + td2 > 0) {
@@ -707,8 +745,11 @@ struct Engine {
         size_t ri = 0, bi = 0;
         for (int l = 0; l < S.n_levels; ++l) {
             for (; ri < rounds.size() && rounds[ri].level == l; ++ri) {
-                ngt::launch_assemble(c, d_ids.p + rounds[ri].dev_off, rounds[ri].count, rounds[ri].max_m, d_child_ptr.p,
-                                     d_child_ids.p, d_inv.p, d_inv_off.p);
+                const bool pe = profile_schur && profile_kind == 1;
+                if (pe) CK(cudaEventRecord(prof_event(), stream));
+                ngt::launch_assemble(c, d_ids.p + rounds[ri].dev_off, rounds[ri].count, rounds[ri].max_m, d_row_base.p,
+                                     d_arow_ptr.p, d_row_child.p, d_row_crow.p, d_rel.p, d_rel_off.p);
+                if (pe) { CK(cudaEventRecord(prof_event(), stream)); st.reserved[0] += 1; }
                 st.n_launches++;
             }
             for (; bi < batches.size() && S.batches[bi].level == l; ++bi) eliminate(c, batches[bi], d_ids.p);
@@ -1265,6 +1306,13 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
     }
     const Symbolic &S = E->S;
 
+    // the analysed structure (fronts, assembly lists, batches, pools) goes to the device beside the slot-table pass
+    device_task.finish();
+    SideTask structure_task;
+    structure_task.start([&] {
+        CK(cudaSetDevice(E->device));
+        E->upload_structure();
+    });
     // CSR by source over present nodes, (src,dst) duplicates resolved "last wins"; rows = present nodes in id order,
     // each worker thread writes the source indices and slots of a contiguous slice of rows
     count_task.finish();
@@ -1318,17 +1366,15 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
     }
     E->n_rows = (int)row_node.size();
     tm.lap("CSR + slot table");
-    device_task.finish();
     CK(cudaSetDevice(E->device));
-    tm.lap("init device + upload rates (joined)");
     E->d_row_ptr.upload(row_ptr);
     E->d_row_node.upload(row_node);
     E->d_korig.upload(korig);
     E->d_dest.upload(dest);
     E->d_tau_dest.upload(tau_dest);
     tm.lap("upload ingest tables");
-    E->upload_structure();
-    tm.lap("upload structure + alloc pools");
+    structure_task.finish();
+    tm.lap("structure upload + pools (joined)");
     E->st.ms_symbolic = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 

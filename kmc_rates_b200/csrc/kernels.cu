@@ -125,6 +125,7 @@ __device__ __forceinline__ void rowpanel_slab_mma(const double *Wd, const double
     }
 }
 
+constexpr unsigned FULL_MASK = 0xffffffffu;
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -1283,50 +1284,85 @@ void launch_ingest_dense(double *pool, long long pool_stride, int nbatch, const 
 }
 
 // =====================================================================================================
-// assembly (extend-add), parent-centric gather: one warp per row of a parent front walks the parent's children in a
-// fixed order and adds the matching child entries (inv maps a parent local index to the child's update index or -1):
-//   parent[a, b] += child[k_c + inv[a], k_c + inv[b]],   parent[a, tau] += child[k_c + inv[a], tau]
-// Every parent entry has exactly one writer, so there are no atomics and the sum order is deterministic; parent rows
-// are written with unit stride.  grid (row tiles of 8, parents of the level, networks).
+// assembly (extend-add), one warp per row of a parent front.  The host lists, per parent row, the (child, child row)
+// pairs that contribute to it, in the fixed order of the children; the warp walks each contributing child row with
+// unit stride and scatters through the child's relative map (child update index -> parent local index):
+//   parent[a, rel_c[j]] += child[k_c + i, k_c + j],   parent[a, tau] += child[k_c + i, tau]     for every (c, i) of row a
+// Every parent row has exactly one writer (its warp), so there are no atomics and the order of the sums is fixed.
+// Work is proportional to the children's update blocks, not to (rows touched) x (parent order).
+// grid (row tiles of 8, parents of the level, networks).
 // =====================================================================================================
+// WPR warps share a parent row, each owning a contiguous range of PARENT columns (the relative maps are ascending, so
+// a warp finds its part of a child row by two binary searches): still one writer per entry, and levels with only a
+// few large parents (the top of the tree) get WPR times the warps in flight.
+template <int WPR>
 __global__ void __launch_bounds__(256)
-assemble_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, const long long *child_ptr,
-                const int *child_ids, const int *inv, const long long *inv_off) {
+assemble_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, const long long *row_base,
+                const long long *row_ptr, const int *row_child, const int *row_crow, const int *__restrict__ rel,
+                const long long *rel_off) {
     pdl_enter();
     const int pid = ids[blockIdx.y];
     const DFront P = fronts[pid];
-    const int a = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a = blockIdx.x * (8 / WPR) + warp / WPR;
     if (a >= P.f) return;
-    const int lane = threadIdx.x & 31;
+    const int part = warp % WPR;
+    const int q = (P.f + WPR - 1) / WPR;                  // parent columns [part*q, part*q + q) belong to this warp
+    const int c_lo = part * q, c_hi = min(P.f, c_lo + q);
     double *base = pool + (long long)blockIdx.z * pool_stride;
     double *prow = base + P.off + (long long)a * P.ld;
-    for (long long ci = child_ptr[pid]; ci < child_ptr[pid + 1]; ++ci) {
-        const int cid = child_ids[ci];
-        const int *iv = inv + inv_off[cid];
-        const int ia = iv[a];
-        if (ia < 0) continue;                      // this child does not touch row a (uniform over the warp)
+    const long long r = row_base[pid] + a;
+    for (long long e = row_ptr[r]; e < row_ptr[r + 1]; ++e) {
+        const int cid = row_child[e];
         const DFront C = fronts[cid];
-        const double *crow = base + C.off + (long long)(C.k + ia) * C.ld + C.k;
-        for (int b = lane; b < P.f; b += 32) {
-            const int ib = iv[b];
-            if (ib >= 0) {
-                const double v = crow[ib];
-                if (v != 0.0) prow[b] += v;
-            }
+        const int m = C.f - C.k;
+        const double *crow = base + C.off + (long long)(C.k + row_crow[e]) * C.ld + C.k;
+        const int *rl = rel + rel_off[cid];
+        int j0 = 0, j1 = m;
+        if (WPR > 1) {                                    // first child column mapped at or beyond c_lo / c_hi
+            int lo = 0, hi = m;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (rl[mid] < c_lo) lo = mid + 1; else hi = mid; }
+            j0 = lo;
+            hi = m;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (rl[mid] < c_hi) lo = mid + 1; else hi = mid; }
+            j1 = lo;
         }
-        if (lane == 0) {
-            const double v = crow[C.f - C.k];      // the child's delta-tau column
+        int j = j0 + lane;
+        for (; j + 96 < j1; j += 128) {                   // four gathers in flight per lane
+            const double v0 = crow[j], v1 = crow[j + 32], v2 = crow[j + 64], v3 = crow[j + 96];
+            const int i0 = rl[j], i1 = rl[j + 32], i2 = rl[j + 64], i3 = rl[j + 96];
+            const double p0 = prow[i0], p1 = prow[i1], p2 = prow[i2], p3 = prow[i3];
+            if (v0 != 0.0) prow[i0] = p0 + v0;
+            if (v1 != 0.0) prow[i1] = p1 + v1;
+            if (v2 != 0.0) prow[i2] = p2 + v2;
+            if (v3 != 0.0) prow[i3] = p3 + v3;
+        }
+        for (; j < j1; j += 32) {
+            const double v = crow[j];
+            if (v != 0.0) prow[rl[j]] += v;
+        }
+        if (part == 0 && lane == 0) {
+            const double v = crow[m];              // the child's delta-tau column
             if (v != 0.0) prow[P.f] += v;
         }
+        __syncwarp();                              // the next child may touch the same entries from other lanes
     }
 }
 
-void launch_assemble(const LaunchCtx &c, const int *ids, int nparents, int max_f, const long long *child_ptr,
-                     const int *child_ids, const int *inv, const long long *inv_off) {
+void launch_assemble(const LaunchCtx &c, const int *ids, int nparents, int max_f, const long long *row_base,
+                     const long long *row_ptr, const int *row_child, const int *row_crow, const int *rel,
+                     const long long *rel_off) {
     if (nparents <= 0 || max_f <= 0) return;
-    dim3 grid((max_f + 7) / 8, nparents, c.nbatch);
-    launch_chain(assemble_kernel, grid, dim3(256), 0, c.stream, c.pool, c.pool_stride, c.fronts, ids, child_ptr, child_ids, inv,
-                 inv_off);
+    // few, large parents: four warps per row
+    if ((long long)nparents * c.nbatch * ((max_f + 7) / 8) < 4 * 148) {
+        dim3 grid((max_f + 1) / 2, nparents, c.nbatch);
+        launch_chain(assemble_kernel<4>, grid, dim3(256), 0, c.stream, c.pool, c.pool_stride, c.fronts, ids, row_base, row_ptr,
+                     row_child, row_crow, rel, rel_off);
+    } else {
+        dim3 grid((max_f + 7) / 8, nparents, c.nbatch);
+        launch_chain(assemble_kernel<1>, grid, dim3(256), 0, c.stream, c.pool, c.pool_stride, c.fronts, ids, row_base, row_ptr,
+                     row_child, row_crow, rel, rel_off);
+    }
 }
 
 // =====================================================================================================

@@ -146,8 +146,9 @@ void launch_ingest_dense(double *pool, long long pool_stride, int nbatch, const 
 // ---- assembly: child update blocks (+ delta-tau column) are added into their parents -----------------------
 // ids: parents of one tree level; child_ptr/child_ids: CSR of children per front; inv/inv_off: per child, parent local
 // index -> child update index or -1
-void launch_assemble(const LaunchCtx &c, const int *ids, int nparents, int max_f, const long long *child_ptr,
-                     const int *child_ids, const int *inv, const long long *inv_off);
+void launch_assemble(const LaunchCtx &c, const int *ids, int nparents, int max_f, const long long *row_base,
+                     const long long *row_ptr, const int *row_child, const int *row_crow, const int *rel,
+                     const long long *rel_off);
 
 // ---- phase 2: build one front per a in the group from the reduced root block -----------------------
 // group = [g0, g0+ng) rows of the root, other = the remaining root rows.  Task t (a = g0 + t) gets a front of
