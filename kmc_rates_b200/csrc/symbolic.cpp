@@ -181,12 +181,16 @@ struct Dissector {
     // 0.35 / 0.40 give 1.08 / 1.11 / 1.19 / 1.29e10 flops, 5.2 / 5.15 / 4.76 / 4.91 ms per step and 48 / 45 / 38 / 37 ms
     // of ordering time
     double min_bal = 0.35;
+    int block_depth = 4;     // subtrees at this depth become the parallel blocks of the symbolic factorisation
     bool trace = std::getenv("NGT_B200_TIMING") != nullptr && std::getenv("NGT_B200_ND_TRACE") != nullptr;
 
     // result of dissecting one subset: nodes in elimination order + supernode sizes
     struct Out {
         std::vector<int32_t> order;
         std::vector<int32_t> sn_size;
+        // ranges [first, last) of supernode indices that form complete dissection subtrees: no supernode outside a
+        // range is a descendant of one inside it, so the symbolic factorisation can process the ranges side by side
+        std::vector<std::pair<int32_t, int32_t> > blocks;
         void emit_glob(const Sub &G, const std::vector<int32_t> &locals) {
             if (locals.empty()) return;
             sn_size.push_back((int32_t)locals.size());
@@ -198,8 +202,10 @@ struct Dissector {
             order.insert(order.end(), G.glob.begin(), G.glob.end());
         }
         void append(Out &o) {
+            const int32_t shift = (int32_t)sn_size.size();
             order.insert(order.end(), o.order.begin(), o.order.end());
             sn_size.insert(sn_size.end(), o.sn_size.begin(), o.sn_size.end());
+            for (auto &b : o.blocks) blocks.emplace_back(b.first + shift, b.second + shift);
         }
     };
 
@@ -264,6 +270,7 @@ struct Dissector {
     void dissect(Sub &G, Out &out, int depth) {
         if (G.n == 0) return;
         if (G.n <= leaf) { out.emit_all(G); return; }
+        const int32_t sn_enter = (int32_t)out.sn_size.size();
         const auto t_enter = std::chrono::steady_clock::now();
         const int32_t n_enter = G.n;
         std::vector<int32_t> lvl(G.n, -1), visit;
@@ -397,6 +404,7 @@ struct Dissector {
             out.sn_size.push_back((int32_t)sep_glob.size());
             out.order.insert(out.order.end(), sep_glob.begin(), sep_glob.end());
         }
+        if (depth == block_depth) out.blocks.emplace_back(sn_enter, (int32_t)out.sn_size.size());
     }
 };
 
@@ -639,14 +647,18 @@ void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
         });
     }
     tm.lap("  symbolic: own neighbours (parallel)");
-    // phase B (in elimination order): add what the children pass up
-    for (int32_t s = 0; s < ns; ++s) {
+    // phase B (children before parents): add what the children pass up.  Complete dissection subtrees (ord.blocks)
+    // are independent of each other and run side by side; what is left (the separators above them and supernodes
+    // that never reached the block depth) follows in elimination order.  A child whose parent lies outside its
+    // block is attached to it afterwards, in increasing child order, so the children lists equal the serial ones.
+    auto process = [&](int32_t s, std::vector<int32_t> &mk, int32_t blk_first, int32_t blk_last,
+                       std::vector<std::pair<int32_t, int32_t> > *deferred) {
         const int32_t first = sn_start[s], last = sn_start[s + 1];
         std::vector<int32_t> &U = upd[s];
-        for (int32_t q : U) mark[q] = s;
+        for (int32_t q : U) mk[q] = s;
         for (int32_t c : kids[s])
             for (int32_t q : upd[c])
-                if (q >= last && mark[q] != s) { mark[q] = s; U.push_back(q); }
+                if (q >= last && mk[q] != s) { mk[q] = s; U.push_back(q); }
         std::sort(U.begin(), U.end());
         Front &F = S.fronts[s];
         F.k = last - first;
@@ -655,9 +667,42 @@ void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
         if (U.empty()) F.parent = -1;
         else if (U[0] >= S.nI) F.parent = ns;
         else F.parent = S.pos_front[U[0]];
-        if (F.parent >= 0) kids[F.parent].push_back(s);
+        if (F.parent >= 0) {
+            if (deferred && (F.parent < blk_first || F.parent >= blk_last)) deferred->emplace_back(F.parent, s);
+            else kids[F.parent].push_back(s);
+        }
+    };
+    {
+        std::vector<char> in_block(ns, 0);
+        const auto &blocks = ord.blocks;
+        const int nb = (int)blocks.size();
+        unsigned hw = std::thread::hardware_concurrency();
+        const int T = (ns < 256 || nb < 2) ? 1 : (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
+        if (T > 1) {
+            for (auto &b : blocks)
+                for (int32_t s = b.first; s < b.second; ++s) in_block[s] = 1;
+            std::vector<std::vector<std::pair<int32_t, int32_t> > > deferred(nb);
+            std::atomic<int> next{0};
+            std::vector<std::thread> th;
+            for (int t = 0; t < T; ++t)
+                th.emplace_back([&] {
+                    std::vector<int32_t> mk(npos, -1);
+                    for (int b = next.fetch_add(1); b < nb; b = next.fetch_add(1))
+                        for (int32_t s = blocks[b].first; s < blocks[b].second; ++s)
+                            process(s, mk, blocks[b].first, blocks[b].second, &deferred[b]);
+                });
+            for (auto &x : th) x.join();
+            std::vector<std::pair<int32_t, int32_t> > all;   // (parent, child)
+            for (auto &d : deferred) all.insert(all.end(), d.begin(), d.end());
+            std::sort(all.begin(), all.end(), [](const std::pair<int32_t, int32_t> &a, const std::pair<int32_t, int32_t> &b) {
+                return a.second < b.second;
+            });
+            for (auto &pc : all) kids[pc.first].push_back(pc.second);
+        }
+        for (int32_t s = 0; s < ns; ++s)
+            if (!in_block[s]) process(s, mark, 0, 0, nullptr);
     }
-    tm.lap("  symbolic: merge children (serial)");
+    tm.lap("  symbolic: merge children (subtrees in parallel)");
     // root
     {
         Front &R = S.fronts[ns];

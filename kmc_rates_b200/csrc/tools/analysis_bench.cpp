@@ -33,7 +33,12 @@ int main(int argc, char **argv) {
         auto t2 = std::chrono::steady_clock::now();
         unsigned long long hsh = 1469598103934665603ULL;   // FNV-1a over the elimination order
         for (int32_t v : S.node_at) { hsh ^= (unsigned long long)(unsigned)v; hsh *= 1099511628211ULL; }
-        std::printf("rep %d: order hash %016llx\n", r, hsh);
+        auto mix = [&](long long v) { hsh ^= (unsigned long long)v; hsh *= 1099511628211ULL; };
+        for (const auto &F : S.fronts) { mix(F.k); mix(F.m); mix(F.parent); mix(F.level); mix(F.off); }
+        for (int32_t v : S.fidx) mix(v);
+        for (int32_t v : S.rel) mix(v);
+        for (int32_t v : S.child_ids) mix(v);
+        std::printf("rep %d: order + structure hash %016llx\n", r, hsh);
         std::printf("rep %d: index %.2f ms  analyse %.2f ms  fronts %zu levels %d max_front %d pool %.3f GB flops %.3e launches~%zu batches\n",
                     r, std::chrono::duration<double, std::milli>(t1 - t0).count(),
                     std::chrono::duration<double, std::milli>(t2 - t1).count(), S.fronts.size(), S.n_levels, S.max_front,
