@@ -50,6 +50,16 @@ void build_adjacency(int64_t n, int64_t nnz, const int64_t *src, const int64_t *
 }
 
 namespace {
+// host worker threads available to the analysis: hardware concurrency, optionally capped by NGT_B200_HOST_THREADS
+// (1 = fully serial; the results do not depend on it, which tests/test_host_analysis.py checks)
+unsigned host_threads() {
+    static const unsigned n = [] {
+        unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        if (const char *e = std::getenv("NGT_B200_HOST_THREADS")) hw = std::min(hw, (unsigned)std::max(1, std::atoi(e)));
+        return hw;
+    }();
+    return n;
+}
 template <class Fn>
 void parallel_ranges(int nthr, int64_t total, Fn &&fn) {
     if (nthr <= 1) { fn(0, (int64_t)0, total); return; }
@@ -61,7 +71,7 @@ void parallel_ranges(int nthr, int64_t total, Fn &&fn) {
 
 void index_edges(int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, EdgeIndex &ix, Adjacency &g,
                  IndexScratch *ws) {
-    unsigned hw = std::thread::hardware_concurrency();
+    unsigned hw = host_threads();
     int T = (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
     while (T > 1 && (double)T * n * 8.0 > 512e6) T /= 2;      // private counters: 8 bytes per node and thread
     if (nnz < 200000) T = 1;
@@ -210,7 +220,7 @@ struct Dissector {
     };
 
     explicit Dissector(int leaf_) : leaf(leaf_) {
-        unsigned hw = std::thread::hardware_concurrency();
+        unsigned hw = host_threads();
         max_par_depth = hw >= 16 ? 4 : hw >= 8 ? 3 : hw >= 4 ? 2 : hw >= 2 ? 1 : 0;
         if (const char *e = std::getenv("NGT_B200_ND_THREADS_DEPTH")) max_par_depth = std::atoi(e);
         if (const char *e = std::getenv("NGT_B200_ND_BALANCE")) min_bal = std::atof(e);
@@ -448,7 +458,7 @@ void finish_layout(Symbolic &S) {
     for (int32_t i = 0; i < nf; ++i) S.rel_off[i + 1] = S.rel_off[i] + (S.fronts[i].parent >= 0 ? S.fronts[i].m : 0);
     S.rel.assign(S.rel_off[nf], -1);
     {
-        unsigned hw = std::thread::hardware_concurrency();
+        unsigned hw = host_threads();
         int T = (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
         if (S.rel.size() < 200000) T = 1;
         std::vector<char> bad(T, 0);
@@ -628,7 +638,7 @@ void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
         for (int32_t p = sn_start[s]; p < sn_start[s + 1]; ++p) S.pos_front[p] = s;
     // phase A (parallel over supernodes): the later neighbours of each supernode's own pivots, sorted and unique
     {
-        unsigned hw = std::thread::hardware_concurrency();
+        unsigned hw = host_threads();
         int T = (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
         if (ns < 256) T = 1;
         parallel_ranges(T, ns, [&](int /*t*/, int64_t s0, int64_t s1) {
@@ -676,7 +686,7 @@ void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
         std::vector<char> in_block(ns, 0);
         const auto &blocks = ord.blocks;
         const int nb = (int)blocks.size();
-        unsigned hw = std::thread::hardware_concurrency();
+        unsigned hw = host_threads();
         const int T = (ns < 256 || nb < 2) ? 1 : (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
         if (T > 1) {
             for (auto &b : blocks)
