@@ -598,15 +598,28 @@ void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
         top.glob = inter;
         for (int32_t i = 0; i < top.n; ++i) newid[inter[i]] = i;
         top.ptr.assign(top.n + 1, 0);
-        top.adj.reserve(g.adj.size());
-        for (int32_t i = 0; i < top.n; ++i) {
-            const int32_t u = inter[i];
-            for (int64_t e = g.ptr[u]; e < g.ptr[u + 1]; ++e) {
-                const int32_t w = newid[g.adj[e]];
-                if (w >= 0) top.adj.push_back(w);
+        // count, prefix, fill: every node's slice of the adjacency is written by one thread
+        const int T = top.n < 20000 ? 1 : (int)std::min(host_threads(), 8u);
+        parallel_ranges(T, top.n, [&](int /*t*/, int64_t i0, int64_t i1) {
+            for (int64_t i = i0; i < i1; ++i) {
+                const int32_t u = inter[i];
+                int32_t c = 0;
+                for (int64_t e = g.ptr[u]; e < g.ptr[u + 1]; ++e) c += newid[g.adj[e]] >= 0;
+                top.ptr[i + 1] = c;
             }
-            top.ptr[i + 1] = (int32_t)top.adj.size();
-        }
+        });
+        for (int32_t i = 0; i < top.n; ++i) top.ptr[i + 1] += top.ptr[i];
+        top.adj.resize(top.ptr[top.n]);
+        parallel_ranges(T, top.n, [&](int /*t*/, int64_t i0, int64_t i1) {
+            for (int64_t i = i0; i < i1; ++i) {
+                const int32_t u = inter[i];
+                int32_t w = top.ptr[i];
+                for (int64_t e = g.ptr[u]; e < g.ptr[u + 1]; ++e) {
+                    const int32_t x = newid[g.adj[e]];
+                    if (x >= 0) top.adj[w++] = x;
+                }
+            }
+        });
     }
     tm.lap("top-level subgraph");
     Dissector::Out ord;
