@@ -304,6 +304,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # several ranks share the host: each analyses its network with its share of the cores (the native host pipeline
+    # reads NGT_B200_HOST_THREADS once, before the first handle is created)
+    if world > 1:
+        os.environ.setdefault("NGT_B200_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — kmc_rates_b200 has no CPU fallback")
     torch.cuda.set_device(local)

@@ -423,7 +423,7 @@ struct Engine {
             for (int p = 0; p < nf; ++p) row_base[p + 1] = row_base[p] + (S.child_ptr[p + 1] > S.child_ptr[p] ? S.fronts[p].f : 0);
             std::vector<long long> row_ptr(row_base[nf] + 1, 0);
             // every parent owns a contiguous range of row_ptr, so parents are counted and filled independently
-            unsigned hw = std::thread::hardware_concurrency();
+            unsigned hw = ngt::host_threads();
             const int nthr = nf < 512 ? 1 : (int)std::max(1u, std::min(hw ? hw : 1u, 8u));
             auto over_parents = [&](auto &&body) {
                 std::vector<std::thread> th;
@@ -1326,7 +1326,7 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
     row_ptr.assign(nrows + 1, 0);
     tau_dest.resize(nrows);
     {
-        unsigned hw = std::thread::hardware_concurrency();
+        unsigned hw = ngt::host_threads();
         int nthr = (int)std::max(1u, std::min(hw ? hw : 1u, 32u));
         if (nrows < 4096) nthr = 1;
         std::vector<std::vector<int32_t> > &marks = W.marks;

@@ -49,7 +49,6 @@ void build_adjacency(int64_t n, int64_t nnz, const int64_t *src, const int64_t *
     g.adj.swap(tmp);
 }
 
-namespace {
 // host worker threads available to the analysis: hardware concurrency, optionally capped by NGT_B200_HOST_THREADS
 // (1 = fully serial; the results do not depend on it, which tests/test_host_analysis.py checks)
 unsigned host_threads() {
@@ -60,6 +59,7 @@ unsigned host_threads() {
     }();
     return n;
 }
+namespace {
 template <class Fn>
 void parallel_ranges(int nthr, int64_t total, Fn &&fn) {
     if (nthr <= 1) { fn(0, (int64_t)0, total); return; }

@@ -73,6 +73,10 @@ struct Symbolic {
     double alg_flops = 0, alg_bytes = 0, schur_flops = 0;
 };
 
+// Worker threads the host analysis may use: hardware concurrency, capped by the environment variable
+// NGT_B200_HOST_THREADS (several ranks sharing one host set it to cores / ranks).
+unsigned host_threads();
+
 // Undirected structure in CSR (no self loops, deduplicated, symmetrised).
 struct Adjacency {
     int64_t n = 0;
