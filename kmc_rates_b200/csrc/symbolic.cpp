@@ -277,18 +277,30 @@ struct Dissector {
         for (int32_t v : members) newid[v] = -1;
     }
 
-    void dissect(Sub &G, Out &out, int depth) {
+    // `known_lvl`: levels of G's nodes in a sweep from node 0 whose visiting order is 0, 1, 2, ... -- true for the
+    // near half of a split, which is numbered in the parent's sweep order from the parent's root: every node there is
+    // discovered by a node of the same half one level down, in the same relative order, so the child's first sweep
+    // would reproduce exactly that numbering and those levels.  It is skipped then (same ordering, bit for bit).
+    void dissect(Sub &G, Out &out, int depth, const std::vector<int32_t> *known_lvl = nullptr) {
         if (G.n == 0) return;
         if (G.n <= leaf) { out.emit_all(G); return; }
         const int32_t sn_enter = (int32_t)out.sn_size.size();
         const auto t_enter = std::chrono::steady_clock::now();
         const int32_t n_enter = G.n;
-        std::vector<int32_t> lvl(G.n, -1), visit;
-        visit.reserve(G.n);
+        std::vector<int32_t> lvl, visit;
         int32_t nlev = 0;
 
         // ---- first sweep: connectivity + a far node
-        bfs(G, 0, lvl, visit, nlev);
+        if (known_lvl && (int32_t)known_lvl->size() == G.n) {
+            lvl = *known_lvl;
+            visit.resize(G.n);
+            for (int32_t i = 0; i < G.n; ++i) visit[i] = i;
+            nlev = lvl.back() + 1;
+        } else {
+            lvl.assign(G.n, -1);
+            visit.reserve(G.n);
+            bfs(G, 0, lvl, visit, nlev);
+        }
         if ((int32_t)visit.size() != G.n) {
             // several components: small ones are packed into leaf-sized bins, large ones dissected on their own
             std::vector<int32_t> comp_start{0};
@@ -353,15 +365,15 @@ struct Dissector {
         if (bestl < 0 || cnt[bestl] * 10 > tot * 6) { out.emit_all(G); return; }
 
         // ---- split in BFS order; separator nodes that do not touch the far side join the near side
-        std::vector<int32_t> P1, P2, sep;
+        std::vector<int32_t> P1, P2, sep, lvl1;   // lvl1: levels of the near half, in its new numbering
         for (int32_t v : visit) {
-            if (lvl[v] < bestl) P1.push_back(v);
+            if (lvl[v] < bestl) { P1.push_back(v); lvl1.push_back(lvl[v]); }
             else if (lvl[v] > bestl) P2.push_back(v);
             else {
                 bool far = false;
                 for (int32_t e = G.ptr[v]; e < G.ptr[v + 1] && !far; ++e)
                     if (lvl[G.adj[e]] == bestl + 1) far = true;
-                if (far) sep.push_back(v); else P1.push_back(v);
+                if (far) sep.push_back(v); else { P1.push_back(v); lvl1.push_back(lvl[v]); }
             }
         }
         std::vector<int32_t> sep_glob(sep.size());
@@ -392,7 +404,7 @@ struct Dissector {
                     std::vector<int32_t> newid(G.n, -1);
                     induce(G, P1, newid, H1);
                 }
-                dissect(H1, out, depth + 1);
+                dissect(H1, out, depth + 1, &lvl1);
             }
             th.join();
             G = Sub();
@@ -407,7 +419,7 @@ struct Dissector {
             G = Sub();                       // release this level before descending
             std::vector<int32_t>().swap(P1);
             std::vector<int32_t>().swap(P2);
-            dissect(H1, out, depth + 1);
+            dissect(H1, out, depth + 1, &lvl1);
             dissect(H2, out, depth + 1);
         }
         if (!sep_glob.empty()) {
