@@ -38,6 +38,11 @@ int main(int argc, char **argv) {
         for (int32_t v : S.fidx) mix(v);
         for (int32_t v : S.rel) mix(v);
         for (int32_t v : S.child_ids) mix(v);
+        for (int64_t v : ix.outptr) mix(v);          // the edge index and the adjacency are threaded too
+        for (int32_t v : ix.ent) mix(v);
+        for (char v : ix.present) mix(v);
+        for (int64_t v : g.ptr) mix(v);
+        for (int32_t v : g.adj) mix(v);
         std::printf("rep %d: order + structure hash %016llx\n", r, hsh);
         std::printf("rep %d: index %.2f ms  analyse %.2f ms  fronts %zu levels %d max_front %d pool %.3f GB flops %.3e launches~%zu batches\n",
                     r, std::chrono::duration<double, std::milli>(t1 - t0).count(),
