@@ -51,7 +51,7 @@ enum {
 /* Options (0 = default everywhere). */
 typedef struct ngt_options {
     int32_t device;          /* CUDA device ordinal */
-    int32_t gemm_path;       /* 0 = FP64 tensor-core DMMA, tile chosen per launch (default); 1 = scalar DFMA (cross-check); 2 = DMMA 128x128 cp.async kernel everywhere */
+    int32_t gemm_path;       /* 0 = FP64 tensor-core DMMA, tile and feed (cp.async / TMA) chosen per launch (default); 1 = scalar DFMA (cross-check); 2 = DMMA with the plain 128x64 cp.async kernel everywhere (cross-check) */
     int32_t leaf_size;       /* nested-dissection leaf size (0 -> 64) */
     int32_t reserved[13];    /* must be zero */
 } ngt_options;
@@ -89,7 +89,7 @@ int ngt_phase_two(ngt_handle h);
 
 /* ---- results ------------------------------------------------------------------------------ */
 int ngt_get_rates(ngt_handle h, double out4[4]);                 /* k_AB, k_BA, k_AB^SS, k_BA^SS */
-int ngt_get_final(ngt_handle h, double *omPxx, double *tau);      /* |A|+|B| each, A then B in the order passed */
+int ngt_get_final(ngt_handle h, double *omPxx, double *tau);      /* nbatch x (|A|+|B|) each, A then B in the order passed */
 int ngt_get_reduced(ngt_handle h, double *P, double *tau);        /* (|A|+|B|)^2 row-major, |A|+|B| */
 int ngt_get_initial_tau(ngt_handle h, double *tau);               /* n */
 int ngt_get_committors(ngt_handle h, double *q);                  /* n; q_A = 0, q_B = 1 */
@@ -127,14 +127,22 @@ int ngt_batch_create_dense_dev(int64_t nbatch, int64_t n, const double *K_dev, i
 /* rates: nbatch x 4 */
 int ngt_batch_get_rates(ngt_handle h, double *out);
 
-/* ---- multi-GPU phase 2: shard the per-a reductions ------------------ */
+/* ---- multi-GPU phase 2: shard the per-a reductions ------------------
+ * Phase 2 is a binary tree of eliminations per group (each a is still reached by eliminating group \ {a}; shared
+ * prefixes are computed once, 4/3 |A|^3 flops instead of the reference's |A|^4).  A rank owns a contiguous block
+ * of every group's members and builds only the tree branches that lead to them. */
 /* Device pointer + size (doubles) of the reduced (|A|+|B|) x ld block incl. tau column, valid after
  * ngt_phase_one; a rank broadcasts it with NCCL into the same buffer of its peers. */
 int ngt_reduced_block_dev(ngt_handle h, double **dptr, int64_t *ndoubles);
-/* Run the per-a reductions only for the a's with (index % nranks) == rank; unfilled entries of the
- * omPxx/tau result are 0 so that an all-reduce(sum) or all-gather merges the shards. */
+/* Run phase 2 only for this rank's members: member i of a group of n belongs to the rank whose block
+ * [r*n/nranks ...) contains i (blocks differ by at most one; remainder to the low ranks).  Entries of other ranks
+ * in the omPxx/tau result are 0, so an all-reduce(sum) merges the shards. */
 int ngt_phase_two_shard(ngt_handle h, int32_t rank, int32_t nranks);
-int ngt_set_final(ngt_handle h, const double *omPxx, const double *tau);   /* install merged results */
+int ngt_set_final(ngt_handle h, const double *omPxx, const double *tau);   /* install merged results, nbatch x (|A|+|B|) each */
+/* Device pointers of the phase-2 results (nbatch x (|A|+|B|) doubles each, valid after ngt_phase_two*): a rank
+ * all-reduces them in place with NCCL and then calls ngt_adopt_final_dev, which downloads them and forms the rates. */
+int ngt_final_dev(ngt_handle h, double **omPxx_dev, double **tau_dev, int64_t *ndoubles);
+int ngt_adopt_final_dev(ngt_handle h);
 
 /* ---- multi-GPU: ONE dense network over several GPUs (SURVEY §8e, config 3 at N > 1) ----------------------
  * 1-D block-cyclic column partition (block = *block of ngt_dist_info) with a panel broadcast per outer block.

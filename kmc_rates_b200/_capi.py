@@ -94,6 +94,8 @@ def lib():
         "ngt_reduced_block_dev": [H, ctypes.POINTER(vp), _i64p],
         "ngt_phase_two_shard": [H, ctypes.c_int32, ctypes.c_int32],
         "ngt_set_final": [H, _f64p, _f64p],
+        "ngt_final_dev": [H, ctypes.POINTER(vp), ctypes.POINTER(vp), _i64p],
+        "ngt_adopt_final_dev": [H],
         "ngt_dist_begin": [H, ctypes.c_int32, ctypes.c_int32],
         "ngt_dist_info": [H, _i64p, _i64p],
         "ngt_dist_rowsum": [H, i64, ctypes.POINTER(vp), _i64p],
@@ -122,7 +124,7 @@ EXPORTED_SYMBOLS = [
     "ngt_destroy", "ngt_compute_rates", "ngt_compute_rates_and_committors", "ngt_phase_one", "ngt_phase_two",
     "ngt_get_rates", "ngt_get_final", "ngt_get_reduced", "ngt_get_initial_tau", "ngt_get_committors", "ngt_get_mfpt",
     "ngt_get_stats", "ngt_timed_steps", "ngt_profile_schur", "ngt_batch_create", "ngt_batch_create_dense", "ngt_batch_create_dense_dev", "ngt_batch_get_rates",
-    "ngt_reduced_block_dev", "ngt_phase_two_shard", "ngt_set_final", "ngt_dist_begin", "ngt_dist_info", "ngt_dist_rowsum",
+    "ngt_reduced_block_dev", "ngt_phase_two_shard", "ngt_set_final", "ngt_final_dev", "ngt_adopt_final_dev", "ngt_dist_begin", "ngt_dist_info", "ngt_dist_rowsum",
     "ngt_dist_factor", "ngt_dist_panel", "ngt_dist_apply", "ngt_dist_root", "ngt_dist_finish", "ngt_trim_device_cache",
     "ngt_last_error",
     "ngt_version",
@@ -209,6 +211,7 @@ class Handle(object):
             if K.dtype != torch.float64:
                 raise ValueError("device rate matrix must be float64")
             K = K.contiguous()
+            torch.cuda.current_stream(K.device).synchronize()   # the producer of K must be done before the engine reads it
             opt = dict(opt)
             opt["device"] = K.device.index or 0
             ptr, dev = ctypes.c_void_p(K.data_ptr()), True
@@ -245,7 +248,11 @@ class Handle(object):
     # ---- setters
     def set_rates(self, k):
         if _is_torch_cuda(k):
+            import torch
+            if k.dtype != torch.float64:
+                raise ValueError("device rate constants must be float64")
             k = k.contiguous()
+            torch.cuda.current_stream(k.device).synchronize()   # the producer of k must be done (engine streams are non-blocking)
             self._keep = [k]
             check(lib().ngt_set_rates_dev(self.h, ctypes.c_void_p(k.data_ptr())))
         else:
@@ -286,11 +293,15 @@ class Handle(object):
         m = self.nA + self.nB
         om, tau = np.zeros(m * self.nbatch), np.zeros(m * self.nbatch)
         check(lib().ngt_get_final(self.h, om.ctypes.data_as(_f64p), tau.ctypes.data_as(_f64p)))
-        return om[:m], tau[:m]
+        if self.nbatch == 1:
+            return om, tau
+        return om.reshape(self.nbatch, m), tau.reshape(self.nbatch, m)
 
     def set_final(self, om, tau):
         om = np.ascontiguousarray(om, np.float64)
         tau = np.ascontiguousarray(tau, np.float64)
+        if om.size != (self.nA + self.nB) * self.nbatch or tau.size != om.size:
+            raise ValueError("set_final needs nbatch x (|A|+|B|) values of 1-P'_aa and of tau'_a")
         check(lib().ngt_set_final(self.h, om.ctypes.data_as(_f64p), tau.ctypes.data_as(_f64p)))
 
     def reduced(self):
@@ -362,6 +373,15 @@ class Handle(object):
 
     def dist_finish(self):
         check(lib().ngt_dist_finish(self.h))
+
+    def final_dev(self):
+        """device pointers (1-P'_aa, tau'_a) and their common length, for an in-place NCCL all-reduce"""
+        a, b, n = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+        check(lib().ngt_final_dev(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)))
+        return a.value, b.value, n.value
+
+    def adopt_final_dev(self):
+        check(lib().ngt_adopt_final_dev(self.h))
 
     def reduced_block_dev(self):
         p = ctypes.c_void_p()

@@ -175,6 +175,7 @@ struct Engine {
     DevBuf<int> d_ids;              // batch ids (phase 1), then extend-add rounds
     DevBuf<int> d_row_child, d_row_crow, d_rel;                 // assembly: per-parent-row contribution lists, relative maps
     DevBuf<long long> d_row_base, d_arow_ptr, d_rel_off;
+    DevBuf<int> d_child_split;   // assembly: per child, where its update columns cross the parent's column quarters
     DevBuf<int> d_fidx;
     DevBuf<long long> d_idx_off;
     std::vector<HostBatch> batches;
@@ -201,7 +202,6 @@ struct Engine {
     long long p2_stride = 0;
     DevBuf<DFront> d_p2fronts;
     DevBuf<int> d_p2ids;
-    std::vector<HostBatch> p2batches[2];
     DevBuf<double> d_om, d_ftau;    // nbatch x m
     // back-substitution
     DevBuf<double> d_x;
@@ -215,7 +215,6 @@ struct Engine {
     std::vector<double> xq;         // nbatch x npos x 2
     bool have_phase1 = false, have_phase2 = false, have_backsub = false, values_loaded = false;
 
-    bool use_big_kernel = std::getenv("NGT_B200_BIG") != nullptr;   // 128 x 128 kernel: measured slower than 2 CTAs/SM of 128 x 64
     bool use_lookahead = std::getenv("NGT_B200_NO_LOOKAHEAD") == nullptr;
     // 2-D tensor maps over the single front of a dense handle (A box 16 x 128, B box 16 x 16, 128-byte swizzle)
     CUtensorMap tmapA{}, tmapB{};
@@ -248,13 +247,8 @@ struct Engine {
         have_tmaps = (ra == CUDA_SUCCESS && rb == CUDA_SUCCESS);
     }
 
-    // Bulk-copy (TMA, cp.async.bulk + mbarrier) fed variant of the Schur kernel: correct, but with one 128-byte bulk
-    // copy per tile row it measured 3x SLOWER than the cp.async ring (dense 16 384: 343 ms vs 117 ms per step) — the
-    // copy engine wants KB-sized boxes.  Opt-in (NGT_B200_TMA=1) until the 2-D tensor-map version replaces it.
-    bool use_tma = std::getenv("NGT_B200_TMA") != nullptr;
-
-    // cp.async.bulk needs 16-byte aligned global addresses and sizes: K a multiple of the 16-pivot stage and starting
-    // on one, tile columns starting on an even index (rows start 64-byte aligned by construction: ld % 8 == 0)
+    // the tensor-map (TMA) fed kernel needs K to be a multiple of the 16-pivot stage and to start on one, and tile
+    // columns starting on an even index (rows start 64-byte aligned by construction: ld % 8 == 0)
     static bool tma_eligible(const HostBatch &b, size_t i, int j, int mode) {
         ngt::Region R;
         if (!ngt::get_region(b.f[i], b.fr.empty() ? 0 : b.fr[i], b.k[i], j, mode, R)) return false;
@@ -459,6 +453,23 @@ struct Engine {
             d_rel.upload(S.rel);
             std::vector<long long> ro(S.rel_off.begin(), S.rel_off.end());
             d_rel_off.upload(ro);
+            // column split points of the children of parents whose rows are shared by ASM_WPR warps (see kernels.cuh)
+            std::vector<int> split((size_t)nf * (ngt::ASM_WPR - 1), 0);
+            for (const Round &rd : rounds) {
+                if (!ngt::assemble_splits_rows(rd.count, nbatch, rd.max_m)) continue;
+                for (int i = 0; i < rd.count; ++i) {
+                    const int p = flat[rd.dev_off + i];
+                    const int q = (S.fronts[p].f + ngt::ASM_WPR - 1) / ngt::ASM_WPR;
+                    for (long long ci = S.child_ptr[p]; ci < S.child_ptr[p + 1]; ++ci) {
+                        const int c = S.child_ids[ci];
+                        const int32_t *rl = S.rel.data() + S.rel_off[c];
+                        for (int part = 1; part < ngt::ASM_WPR; ++part)
+                            split[(size_t)c * (ngt::ASM_WPR - 1) + part - 1] =
+                                (int)(std::lower_bound(rl, rl + S.fronts[c].m, part * q) - rl);
+                    }
+                }
+            }
+            d_child_split.upload(split);
         }
         d_ids.upload(flat);
         d_fidx.upload(S.fidx);
@@ -492,45 +503,110 @@ struct Engine {
         st.alg_bytes = S.alg_bytes * nbatch;
     }
 
-    // phase-2 task fronts: group g (0 = A, 1 = B), task t -> front of order ng+1 with ng-1 pivots
-    void build_phase2_structure() {
+    // Phase-2 plan: per group a binary tree of eliminations (kernels.cu, "phase 2").  Level d holds the fronts whose
+    // source is a front of level d-1 (level 0: the reduced root block); both groups share the launches of a level.
+    // Sharded runs (rank, nranks) own the members [lo, hi) of every group given by a contiguous split and build only
+    // the fronts whose kept set meets their range.
+    struct P2Level { size_t task0; int ntask; int max_f; std::vector<HostBatch> batches; };
+    std::vector<P2Level> p2levels;
+    int p2_nleaf = 0, p2_rank = -1, p2_nranks = 0;
+    DevBuf<ngt::P2Task> d_p2tasks;
+    DevBuf<int> d_p2leaf_front, d_p2leaf_out;
+
+    static void shard_span(int n, int rank, int nranks, int &lo, int &hi) {
+        const int base = n / nranks, extra = n % nranks;
+        lo = rank * base + std::min(rank, extra);
+        hi = lo + base + (rank < extra ? 1 : 0);
+    }
+
+    void build_phase2_structure(int rank = 0, int nranks = 1) {
+        if (rank == p2_rank && nranks == p2_nranks) return;
+        if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }   // the captured step used the old plan
+        struct Node { int group, lo, hi, front; };   // kept members [lo, hi) of `group`, front that produced them
         std::vector<DFront> pf;
-        std::vector<int> flat;
+        std::vector<ngt::P2Task> tasks;
+        std::vector<int> flat, leaf_front, leaf_out;
+        p2levels.clear();
         long long off = 0;
         const int ngs[2] = {(int)S.nA, (int)S.nB};
-        for (int g = 0; g < 2; ++g) {
-            p2batches[g].clear();
-            const int ng = ngs[g];
-            HostBatch hb;
-            for (int t = 0; t < ng; ++t) {
-                DFront F{};
-                F.f = ng + 1;
-                F.k = ng - 1;
-                F.ld = ((F.f + 1 + 7) / 8) * 8;
-                F.off = off;
-                F.parent = -1;
-                off += (long long)F.f * F.ld;
-                off = ((off + 15) / 16) * 16;
-                if (hb.ids.size() == 32768) {
-                    p2batches[g].push_back(hb);
-                    hb = HostBatch();
+        const int g0s[2] = {0, (int)S.nA};
+        int own_lo[2], own_hi[2];
+        for (int g = 0; g < 2; ++g) shard_span(ngs[g], rank, nranks, own_lo[g], own_hi[g]);
+        auto add_front = [&](P2Level &L, int group, int src, int src_k, int npk, int t_off, int t_len) {
+            DFront F{};
+            F.f = npk + 1;
+            F.k = npk - t_len;
+            F.ld = ((F.f + 1 + 7) / 8) * 8;
+            F.off = off;
+            F.parent = -1;
+            off += (long long)F.f * F.ld;
+            off = ((off + 15) / 16) * 16;
+            ngt::P2Task t{};
+            t.src = src; t.src_k = src_k; t.npk = npk; t.t_off = t_off; t.t_len = t_len;
+            t.o0 = group == 0 ? (int)S.nA : 0;
+            t.no = group == 0 ? (int)S.nB : (int)S.nA;
+            const int id = (int)pf.size();
+            pf.push_back(F);
+            tasks.push_back(t);
+            L.ntask++;
+            L.max_f = std::max(L.max_f, F.f);
+            if (F.k > 0) {
+                if (L.batches.empty() || L.batches.back().ids.size() == 32768) {
+                    L.batches.emplace_back();
+                    L.batches.back().dev_off = flat.size();
                 }
-                if (hb.ids.empty()) hb.dev_off = flat.size();
-                hb.ids.push_back((int)pf.size());
-                hb.f.push_back(F.f);
-                hb.k.push_back(F.k);
+                HostBatch &hb = L.batches.back();
+                hb.ids.push_back(id); hb.f.push_back(F.f); hb.k.push_back(F.k);
                 hb.max_k = std::max(hb.max_k, F.k);
-                flat.push_back((int)pf.size());
-                pf.push_back(F);
+                flat.push_back(id);
             }
-            if (!hb.ids.empty()) p2batches[g].push_back(hb);
-            for (auto &b : p2batches[g]) maxfb = std::max(maxfb, (int)b.ids.size());
+            return id;
+        };
+        // level 0: every group as a whole, read from the root block (a group of one member is its own leaf)
+        std::vector<Node> cur, nxt;
+        for (int g = 0; g < 2; ++g)
+            if (ngs[g] > 0 && own_hi[g] > own_lo[g]) cur.push_back(Node{g, 0, ngs[g], -1});
+        while (!cur.empty()) {
+            P2Level L{tasks.size(), 0, 0, {}};
+            nxt.clear();
+            for (const Node &nd : cur) {
+                const int h = nd.hi - nd.lo;
+                const int src_k = nd.front < 0 ? g0s[nd.group] : pf[nd.front].k;
+                auto child = [&](int lo, int hi) {
+                    if (hi <= own_lo[nd.group] || lo >= own_hi[nd.group]) return;   // another rank's members
+                    const int id = add_front(L, nd.group, nd.front, src_k, h, lo - nd.lo, hi - lo);
+                    if (hi - lo == 1) { leaf_front.push_back(id); leaf_out.push_back(g0s[nd.group] + lo); }
+                    else nxt.push_back(Node{nd.group, lo, hi, id});
+                };
+                if (h == 1) child(nd.lo, nd.hi);           // only at level 0: a group with a single member
+                else {
+                    const int mid = nd.lo + (h + 1) / 2;
+                    child(nd.lo, mid);
+                    child(mid, nd.hi);
+                }
+            }
+            if (L.ntask > 65535) throw InvalidError("A or B too large for phase 2 (more than 65535 fronts in one tree level)");
+            if (L.ntask > 0) p2levels.push_back(std::move(L));
+            cur.swap(nxt);
         }
+        for (auto &L : p2levels)
+            for (auto &b : L.batches) maxfb = std::max(maxfb, (int)b.ids.size());
+        p2_nleaf = (int)leaf_front.size();
         p2_stride = off;
         d_p2fronts.upload(pf);
         h_p2fronts = pf;
+        d_p2tasks.upload(tasks);
         d_p2ids.upload(flat);
-        d_p2pool.alloc((size_t)p2_stride * nbatch);
+        d_p2leaf_front.upload(leaf_front);
+        d_p2leaf_out.upload(leaf_out);
+        d_p2pool.alloc((size_t)std::max<long long>(p2_stride, 1) * nbatch);
+        // wbuf / rsbuf are sized by the largest batch of either phase
+        if (d_wbuf.n < (size_t)nbatch * maxfb * ngt::NB_INNER * ngt::NB_INNER)
+            d_wbuf.alloc((size_t)nbatch * maxfb * ngt::NB_INNER * ngt::NB_INNER);
+        if (d_rsbuf.p && d_rsbuf.n < (size_t)nbatch * maxfb * maxchunks * ngt::NB_INNER)
+            d_rsbuf.alloc((size_t)nbatch * maxfb * maxchunks * ngt::NB_INNER);
+        p2_rank = rank;
+        p2_nranks = nranks;
     }
 
     // ---------------------------------------------------------------------------------------------
@@ -631,22 +707,12 @@ struct Engine {
             }
             const bool d2_half = half_tiles(td2);
             if (d2_half) td2 = max_tiles(b, j, ngt::MODE_D2, 64, tn, dummy);
-            // large trailing regions run on the 128 x 128 kernel when they fill the machine (>= 2 waves of big
-            // tiles); small regions keep the 128 x 64 kernel (more CTAs)
             ngt::LaunchCtx c2 = cj;
             if (d2_half) c2.tile_m = 64;
             bool d2_async = false;
             if (td2 > 0 && !d2_half) {
                 long long live = 0;
                 for (int i = 0; i < nfb; ++i) live += (b.k[i] > j);
-                const int tbig = max_tiles(b, j, ngt::MODE_D2, ngt::update_tile_m(2), ngt::update_tile_n(2), dummy);
-                if (opt.gemm_path == 0 && use_big_kernel && (long long)tbig * live * nbatch >= 2 * 148) {
-                    c2.gemm_path = 2;
-                    td2 = tbig;
-                }
-                // single-front trailing updates whose operands meet the bulk-copy alignment rules are fed by TMA
-                if (opt.gemm_path == 0 && use_tma && c2.gemm_path == 0 && nfb == 1 && tma_eligible(b, 0, j, ngt::MODE_D2))
-                    c2.gemm_path = 3;
                 // look-ahead: a trailing update big enough to keep the GPU busy runs on the second stream while
                 // the next outer block's panels proceed on the main stream
                 d2_async = use_lookahead && (long long)td2 * live * nbatch >= 148;
@@ -748,7 +814,7 @@ struct Engine {
                 const bool pe = profile_schur && profile_kind == 1;
                 if (pe) CK(cudaEventRecord(prof_event(), stream));
                 ngt::launch_assemble(c, d_ids.p + rounds[ri].dev_off, rounds[ri].count, rounds[ri].max_m, d_row_base.p,
-                                     d_arow_ptr.p, d_row_child.p, d_row_crow.p, d_rel.p, d_rel_off.p);
+                                     d_arow_ptr.p, d_row_child.p, d_row_crow.p, d_rel.p, d_rel_off.p, d_child_split.p);
                 if (pe) { CK(cudaEventRecord(prof_event(), stream)); st.reserved[0] += 1; }
                 st.n_launches++;
             }
@@ -786,40 +852,23 @@ struct Engine {
     void phase_two_enqueue(int rank = 0, int nranks = 1) {
         if (!have_phase1) throw StateError("phase_two called before phase_one");
         CK(cudaSetDevice(device));
+        if (!capturing) build_phase2_structure(rank, nranks);
         if (!capturing) CK(cudaEventRecord(ev[3], stream));
         const DFront R{S.fronts[S.root_id].off, S.fronts[S.root_id].f, 0, S.fronts[S.root_id].ld, -1};
         ngt::LaunchCtx c1 = ctx(d_pool.p, pool_stride, d_fronts.p);
         ngt::LaunchCtx c2 = ctx(d_p2pool.p, p2_stride, d_p2fronts.p);
-        const int nA = (int)S.nA, nB = (int)S.nB;
-        CK(cudaMemsetAsync(d_p2pool.p, 0, (size_t)p2_stride * nbatch * sizeof(double), stream));
-        for (int g = 0; g < 2; ++g) {
-            const int ng = g == 0 ? nA : nB, g0 = g == 0 ? 0 : nA, o0 = g == 0 ? nA : 0, no = g == 0 ? nB : nA;
-            const int task0 = g == 0 ? 0 : nA;
-            ngt::launch_phase2_gather(c1, R, g0, ng, o0, no, d_p2pool.p, p2_stride, d_p2fronts.p, task0, ng, rank, nranks);
+        CK(cudaMemsetAsync(d_p2pool.p, 0, (size_t)std::max<long long>(p2_stride, 1) * nbatch * sizeof(double), stream));
+        // members owned by other ranks report 0, so that an all-reduce(sum) merges the shards
+        CK(cudaMemsetAsync(d_om.p, 0, (size_t)nbatch * m * sizeof(double), stream));
+        CK(cudaMemsetAsync(d_ftau.p, 0, (size_t)nbatch * m * sizeof(double), stream));
+        for (const P2Level &L : p2levels) {
+            ngt::launch_phase2_gather(c1, R, d_p2pool.p, p2_stride, d_p2fronts.p, d_p2tasks.p, (int)L.task0, L.ntask, L.max_f);
             st.n_launches++;
-            // sharded run: fronts of other ranks stay zero; their pivots would be 0/0, so eliminate only owned tasks
-            if (nranks > 1) {
-                for (const auto &b : p2batches[g]) {
-                    HostBatch mine;
-                    mine.dev_off = 0;
-                    std::vector<int> ids;
-                    for (size_t i = 0; i < b.ids.size(); ++i)
-                        if (((b.ids[i] - task0) % nranks) == rank) {
-                            mine.ids.push_back(b.ids[i]); mine.f.push_back(b.f[i]); mine.k.push_back(b.k[i]);
-                            mine.max_k = std::max(mine.max_k, b.k[i]);
-                        }
-                    if (mine.ids.empty()) continue;
-                    shard_ids.emplace_back();
-                    shard_ids.back().upload(mine.ids);
-                    eliminate(c2, mine, shard_ids.back().p);
-                }
-            } else {
-                for (const auto &b : p2batches[g]) eliminate(c2, b, d_p2ids.p);
-            }
-            ngt::launch_phase2_collect(c2, d_p2pool.p, p2_stride, d_p2fronts.p, task0, ng, ng, d_om.p, d_ftau.p, m, g0,
-                                       rank, nranks);
-            st.n_launches++;
+            for (const auto &b : L.batches) eliminate(c2, b, d_p2ids.p);
         }
+        ngt::launch_phase2_collect(c2, d_p2pool.p, p2_stride, d_p2fronts.p, d_p2leaf_front.p, d_p2leaf_out.p, p2_nleaf,
+                                   d_om.p, d_ftau.p, m);
+        st.n_launches++;
         CK(cudaGetLastError());
         if (!capturing) CK(cudaEventRecord(ev[4], stream));
     }
@@ -838,6 +887,7 @@ struct Engine {
             return;
         }
         CK(cudaSetDevice(device));
+        build_phase2_structure(0, 1);      // (destroys a graph captured with a sharded phase-2 plan)
         if (!graph_exec || graph_dK != d_K) {
             if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
             cudaGraph_t g = nullptr;
@@ -873,7 +923,6 @@ struct Engine {
         CK(cudaMemcpyAsync(final_tau.data(), d_ftau.p, final_tau.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
         download_root();
         check_errflag("phase two");
-        shard_ids.clear();
         if (!last_step_graph) {
             float ms = 0;
             cudaEventElapsedTime(&ms, ev[0], ev[1]); st.ms_ingest = ms;
@@ -883,7 +932,6 @@ struct Engine {
         have_phase2 = true;
         if (nranks == 1) finish_rates();
     }
-    std::vector<DevBuf<int> > shard_ids;
 
     // reference ngt.hpp:444-513
     void finish_rates() {
@@ -944,8 +992,13 @@ struct Engine {
         d_dfronts.alloc(3);            // [0] panel front, [1]/[2] big matrix with panel buffer 0/1 as A operand
         d_dids.upload(std::vector<int>{0, 1, 2});
         d2_pending = false;
-        maxfb = std::max(maxfb, ngt::NB_OUTER / ngt::NB_INNER);
-        d_wbuf.alloc((size_t)nbatch * maxfb * ngt::NB_INNER * ngt::NB_INNER);
+        if ((int)(ngt::NB_OUTER / ngt::NB_INNER) > maxfb) {
+            // wbuf grows (one W per inner panel of an outer block): a step graph captured earlier has the old pointer
+            // and stride baked in
+            if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+            maxfb = ngt::NB_OUTER / ngt::NB_INNER;
+            d_wbuf.alloc((size_t)nbatch * maxfb * ngt::NB_INNER * ngt::NB_INNER);
+        }
         st.n_launches = 0;
         st.schur_flops = 0;
         ingest();
@@ -1396,6 +1449,9 @@ void build_dense(Engine *E, int64_t n, const double *K, bool on_device, int64_t 
     E->make_tensor_maps();
     if (K) {
         if (on_device) {
+            // the caller's producer (a torch kernel on any stream) must have finished before the engine's own
+            // non-blocking streams read K
+            CK(cudaDeviceSynchronize());
             E->d_K = K;
         } else {
             E->d_K_owned.alloc((size_t)n * n * E->nbatch);
@@ -1424,6 +1480,9 @@ int guard(Fn &&fn) {
     } catch (const NumericError &e) {
         g_err = e.what();
         return NGT_E_NUMERIC;
+    } catch (const ngt::LaunchFailure &e) {
+        g_err = e.what();
+        return NGT_E_CUDA;
     } catch (const std::exception &e) {
         g_err = e.what();
         return NGT_E_INVALID;
@@ -1433,6 +1492,13 @@ int guard(Fn &&fn) {
 Engine *eng(ngt_handle h) {
     if (!h) throw InvalidError("null handle");
     return reinterpret_cast<Engine *>(h);
+}
+// getters that return one network's worth of data refuse batched handles instead of silently answering for network 0
+Engine *eng_single(ngt_handle h, const char *what) {
+    Engine *E = eng(h);
+    if (E->nbatch != 1)
+        throw InvalidError(std::string(what) + " returns one network; this handle holds a batch (use the ngt_batch_* getters)");
+    return E;
 }
 
 }  // namespace
@@ -1508,16 +1574,23 @@ static int set_rates_any(ngt_handle h, const double *k, bool dev) {
         if (!k) throw InvalidError("null rate pointer");
         CK(cudaSetDevice(E->device));
         const size_t cnt = (size_t)E->nnz * E->nbatch;
+        // device pointers: whatever produced k (on any stream of the caller) must be complete before the engine's
+        // non-blocking streams touch it; the engine's own previous step must be done before its inputs change
+        if (dev) CK(cudaDeviceSynchronize());
+        else CK(cudaStreamSynchronize(E->stream));
         if (E->dense) {
             if (dev) {
                 E->d_K = k;
             } else {
                 if (!E->d_K_owned.p) E->d_K_owned.alloc(cnt);
-                CK(cudaMemcpy(E->d_K_owned.p, k, cnt * sizeof(double), cudaMemcpyHostToDevice));
+                CK(cudaMemcpyAsync(E->d_K_owned.p, k, cnt * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+                CK(cudaStreamSynchronize(E->stream));
                 E->d_K = E->d_K_owned.p;
             }
         } else {
-            CK(cudaMemcpy(E->d_k.p, k, cnt * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+            CK(cudaMemcpyAsync(E->d_k.p, k, cnt * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                               E->stream));
+            CK(cudaStreamSynchronize(E->stream));
         }
         E->values_loaded = true;
         E->have_phase1 = E->have_phase2 = E->have_backsub = false;
@@ -1587,7 +1660,7 @@ int ngt_compute_rates_and_committors(ngt_handle h) {
 
 int ngt_get_rates(ngt_handle h, double out4[4]) {
     return guard([&] {
-        Engine *E = eng(h);
+        Engine *E = eng_single(h, "ngt_get_rates");
         if (!E->have_phase2 || E->rates.empty()) throw StateError("compute_rates has not been called");
         for (int i = 0; i < 4; ++i) out4[i] = E->rates[i];
     });
@@ -1605,8 +1678,8 @@ int ngt_get_final(ngt_handle h, double *omPxx, double *tau) {
     return guard([&] {
         Engine *E = eng(h);
         if (!E->have_phase2) throw StateError("compute_rates has not been called");
-        std::memcpy(omPxx, E->final_om.data(), (size_t)E->m * sizeof(double));
-        std::memcpy(tau, E->final_tau.data(), (size_t)E->m * sizeof(double));
+        std::memcpy(omPxx, E->final_om.data(), (size_t)E->m * E->nbatch * sizeof(double));
+        std::memcpy(tau, E->final_tau.data(), (size_t)E->m * E->nbatch * sizeof(double));
     });
 }
 
@@ -1620,9 +1693,31 @@ int ngt_set_final(ngt_handle h, const double *omPxx, const double *tau) {
     });
 }
 
-int ngt_get_reduced(ngt_handle h, double *P, double *tau) {
+int ngt_final_dev(ngt_handle h, double **om, double **tau, int64_t *ndoubles) {
     return guard([&] {
         Engine *E = eng(h);
+        if (!E->have_phase2) throw StateError("phase two has not been run");
+        *om = E->d_om.p;
+        *tau = E->d_ftau.p;
+        *ndoubles = (int64_t)E->m * E->nbatch;
+    });
+}
+
+int ngt_adopt_final_dev(ngt_handle h) {
+    return guard([&] {
+        Engine *E = eng(h);
+        if (!E->have_phase2) throw StateError("phase two has not been run");
+        CK(cudaSetDevice(E->device));
+        CK(cudaDeviceSynchronize());     // the caller's collective ran on a stream of its own
+        CK(cudaMemcpy(E->final_om.data(), E->d_om.p, E->final_om.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(E->final_tau.data(), E->d_ftau.p, E->final_tau.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        E->finish_rates();
+    });
+}
+
+int ngt_get_reduced(ngt_handle h, double *P, double *tau) {
+    return guard([&] {
+        Engine *E = eng_single(h, "ngt_get_reduced");
         if (!E->have_phase1) throw StateError("phase one has not been run");
         if (!E->have_phase2) {
             E->download_root();
@@ -1637,7 +1732,7 @@ int ngt_get_reduced(ngt_handle h, double *P, double *tau) {
 
 int ngt_get_initial_tau(ngt_handle h, double *tau) {
     return guard([&] {
-        Engine *E = eng(h);
+        Engine *E = eng_single(h, "ngt_get_initial_tau");
         if (!E->have_phase1) throw StateError("phase one has not been run");
         if (E->tau0.empty()) {
             E->download_root();
@@ -1649,7 +1744,7 @@ int ngt_get_initial_tau(ngt_handle h, double *tau) {
 
 static int get_x(ngt_handle h, double *out, int which) {
     return guard([&] {
-        Engine *E = eng(h);
+        Engine *E = eng_single(h, which == 0 ? "ngt_get_committors" : "ngt_get_mfpt");
         if (!E->have_backsub) E->backsub();
         const double nan = std::nan("");
         for (int64_t u = 0; u < E->n; ++u) {

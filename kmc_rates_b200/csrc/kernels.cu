@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 namespace ngt {
 
@@ -33,6 +34,11 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// a launch that the runtime refuses (bad configuration, missing attribute) must not pass silently
+static void check_launch(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) throw LaunchFailure(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
 static bool use_pdl() {
     static const bool on = std::getenv("NGT_B200_NO_PDL") == nullptr;
     return on;
@@ -52,7 +58,7 @@ static void launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t s
         cfg.attrs = at;
         cfg.numAttrs = 1;
     }
-    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+    check_launch(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...), "cudaLaunchKernelEx");
 }
 
 // same, as thread-block clusters of `cluster_x` CTAs along x
@@ -78,7 +84,7 @@ static void launch_chain_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, 
     }
     cfg.attrs = at;
     cfg.numAttrs = na;
-    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+    check_launch(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...), "cudaLaunchKernelEx (cluster)");
 }
 
 // single-front launches carry their front descriptor in the kernel parameters (saves two dependent global loads)
@@ -125,7 +131,6 @@ __device__ __forceinline__ void rowpanel_slab_mma(const double *Wd, const double
     }
 }
 
-constexpr unsigned FULL_MASK = 0xffffffffu;
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -766,15 +771,7 @@ update_dmma_kernel(double *pool, long long pool_stride, const DFront *fronts, co
     NGT_UCLK(5);
 }
 
-// =====================================================================================================
-// Schur update fed by the bulk-copy engine (TMA, `cp.async.bulk` -> SASS UBLKCP) with mbarrier hand-over:
-// warp 8 is the producer (it arms the stage's "full" mbarrier with the byte count and issues one bulk copy per tile
-// row: 128 B of A per row, up to 512 B of B per pivot), warps 0-7 are the consumers (wait on "full", LDS + DMMA,
-// arrive on "empty").  No thread of the math warps touches addresses or predicates of the global loads.
-// Same tile geometry, shared-memory layout and accumulation order as update_dmma_kernel, so results are bitwise
-// equal.  Used for single-front trailing updates whose operands satisfy the 16-byte alignment rules of bulk
-// copies (full outer blocks; the host checks, see Engine::tma_eligible); everything else stays on cp.async.
-// =====================================================================================================
+// mbarrier / bulk-copy helpers of the tensor-map fed Schur kernel below
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -794,116 +791,6 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-constexpr int TMA_THREADS = 288;   // 8 math warps + 1 producer warp
-
-__global__ void __maxnreg__(112)
-update_dmma_tma_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode_in,
-                       int split, KOpt ko) {
-    const DFront F = fronts[ids[blockIdx.y]];
-    Region R;
-    int mode = mode_in, tile = blockIdx.x;
-    if (mode_in == MODE_AB) {
-        if (tile < split) mode = MODE_A; else { mode = MODE_B; tile -= split; }
-    } else if (mode_in == MODE_D1) {
-        if (tile < split) mode = MODE_D1A; else { mode = MODE_D1B; tile -= split; }
-    }
-    if (!get_region(F.f, F.fr, F.k, j, mode, R)) return;
-    const int tiles_c = (R.c1 - R.c0 + TN - 1) / TN;
-    const int tiles_r = (R.r1 - R.r0 + TM - 1) / TM;
-    const int tr = tile / tiles_c, tc = tile % tiles_c;
-    if (tr >= tiles_r) return;
-    double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
-    const double *MA = F.a_ld ? pool + (long long)blockIdx.z * pool_stride + F.a_off : M;
-    const long long lda = F.a_ld ? F.a_ld : F.ld;
-    const int rb = R.r0 + tr * TM, cb = R.c0 + tc * TN;
-    const long long ld = F.ld;
-    if (ko.own_G > 1 && !owned_col(ko, cb, F.f) && !owned_col(ko, min(cb + TN, R.c1) - 1, F.f)) return;
-
-    extern __shared__ double smem[];
-    __shared__ unsigned long long full_bar[TSTG], empty_bar[TSTG];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < TSTG; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 8); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int nk = (R.k1 - R.k0) / TK;                      // host guarantees K % 16 == 0
-    const int arows = min(TM, R.r1 - rb);                   // tile rows that exist
-    const int bcols = min(TN, ((R.c1 - cb) + 1) & ~1);      // even count; row padding (ld >= f+1 rounded to 8) covers it
-    const unsigned stage_bytes = (unsigned)(arows * TK * 8 + TK * bcols * 8);
-
-    if (warp == 8) {
-        // ===== producer =====
-        for (int kt = 0; kt < nk; ++kt) {
-            const int stg = kt % TSTG;
-            if (kt >= TSTG) mbar_wait(&empty_bar[stg], ((kt / TSTG) - 1) & 1);
-            const int kb = R.k0 + kt * TK;
-            double *As = smem + stg * TSTAGE_DOUBLES;
-            double *Bs = As + TM * AS_LD;
-            if (lane == 0) mbar_expect_tx(&full_bar[stg], stage_bytes);
-            __syncwarp();
-            for (int r = lane; r < arows; r += 32)
-                bulk_g2s(As + r * AS_LD, MA + (long long)(rb + r) * lda + kb, TK * 8, &full_bar[stg]);
-            if (lane < TK)
-                bulk_g2s(Bs + lane * BS_LD, M + (long long)(kb + lane) * ld + cb, bcols * 8, &full_bar[stg]);
-        }
-        return;
-    }
-    // ===== consumers =====
-    const int wm = warp & 3, wn = warp >> 2;
-    const int g = lane >> 2, t4 = lane & 3;
-    double acc[4][4][2];
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {
-        const int r = rb + wm * 32 + mi * 8 + g;
-        const double *row = M + (long long)r * ld;
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
-            acc[mi][ni][0] = (r < R.r1 && c0 < R.c1) ? row[c0] : 0.0;
-            acc[mi][ni][1] = (r < R.r1 && c0 + 1 < R.c1) ? row[c0 + 1] : 0.0;
-        }
-    }
-    for (int kt = 0; kt < nk; ++kt) {
-        const int stg = kt % TSTG;
-        mbar_wait(&full_bar[stg], (kt / TSTG) & 1);
-        const double *As = smem + stg * TSTAGE_DOUBLES;
-        const double *Bs = As + TM * AS_LD;
-#pragma unroll
-        for (int k4 = 0; k4 < TK / 4; ++k4) {
-            double a[4], b[4];
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi) a[mi] = As[(wm * 32 + mi * 8 + g) * AS_LD + k4 * 4 + t4];
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(k4 * 4 + t4) * BS_LD + wn * 32 + ni * 8 + g];
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stg]);
-    }
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {
-        const int r = rb + wm * 32 + mi * 8 + g;
-        if (r >= R.r1) continue;
-        double *row = M + (long long)r * ld;
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
-            if (c0 < R.c1 && owned_col(ko, c0, F.f)) row[c0] = acc[mi][ni][0];
-            if (c0 + 1 < R.c1 && owned_col(ko, c0 + 1, F.f)) row[c0 + 1] = acc[mi][ni][1];
-        }
-    }
-}
-
 // =====================================================================================================
 // Schur update fed by 2-D tensor-map TMA (`cp.async.bulk.tensor.2d` -> SASS UTMALDG) for large single-front
 // trailing updates.  Per 16-pivot stage the producer warp issues FIVE copies: one 16 x 128 box of A (16 KB) and four
@@ -1039,126 +926,8 @@ void launch_update_tmap(const LaunchCtx &c, const int *ids, int j, int mode, int
                  c.ko, *static_cast<const CUtensorMap *>(tmA), *static_cast<const CUtensorMap *>(tmB));
 }
 
-// =====================================================================================================
-// Large-region Schur update: CTA tile 128 x 128, 16 warps as 4 (M) x 4 (N), warp tile 32 x 32 = 4 x 4 DMMA tiles,
-// K staged 16 at a time through a 4-stage cp.async ring (global -> shared without touching registers), so loads
-// of stage t+3 overlap the DMMAs of stage t.  The accumulators start from the C tile itself (loaded while the
-// pipeline fills), so the epilogue is a plain store: C = C + A B with no read-modify-write tail.
-// =====================================================================================================
-constexpr int BM = 128, BN = 128, BK = 16, STG = 4;
-constexpr int BA_LD = BK + 4, BB_LD = BN + 4;
-constexpr int STAGE_DOUBLES = BM * BA_LD + BK * BB_LD;
-
-__global__ void __launch_bounds__(512, 1)
-update_dmma_big_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, int j, int mode_in,
-                       int split, KOpt ko) {
-    const DFront F = fronts[ids[blockIdx.y]];
-    Region R;
-    int mode = mode_in, tile = blockIdx.x;
-    if (mode_in == MODE_AB) {
-        if (tile < split) mode = MODE_A; else { mode = MODE_B; tile -= split; }
-    } else if (mode_in == MODE_D1) {
-        if (tile < split) mode = MODE_D1A; else { mode = MODE_D1B; tile -= split; }
-    }
-    if (!get_region(F.f, F.fr, F.k, j, mode, R)) return;
-    const int tiles_c = (R.c1 - R.c0 + BN - 1) / BN;
-    const int tiles_r = (R.r1 - R.r0 + BM - 1) / BM;
-    const int tr = tile / tiles_c, tc = tile % tiles_c;
-    if (tr >= tiles_r) return;
-    double *M = pool + (long long)blockIdx.z * pool_stride + F.off;
-    const double *MA = F.a_ld ? pool + (long long)blockIdx.z * pool_stride + F.a_off : M;
-    const long long lda = F.a_ld ? F.a_ld : F.ld;
-    const int rb = R.r0 + tr * BM, cb = R.c0 + tc * BN;
-    const long long ld = F.ld;
-    if (ko.own_G > 1 && !owned_col(ko, cb, F.f) && !owned_col(ko, min(cb + BN, R.c1) - 1, F.f)) return;
-
-    extern __shared__ double smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wm = warp & 3, wn = warp >> 2;          // 16 warps as 4 (M) x 4 (N), warp tile 32 x 32
-    const int g = lane >> 2, t4 = lane & 3;
-
-    // accumulators = C tile (issued first: their latency hides behind the pipeline prologue)
-    double acc[4][4][2];
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {
-        const int r = rb + wm * 32 + mi * 8 + g;
-        const double *row = M + (long long)r * ld;
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
-            acc[mi][ni][0] = (r < R.r1 && c0 < R.c1) ? row[c0] : 0.0;
-            acc[mi][ni][1] = (r < R.r1 && c0 + 1 < R.c1) ? row[c0 + 1] : 0.0;
-        }
-    }
-
-    const int nk = (R.k1 - R.k0 + BK - 1) / BK;
-    // per-thread load slots: A element (row ar + 32 i, pivot kb + ak), B element (pivot kb + bk + 4 i, column bc)
-    const int ar = threadIdx.x >> 4, ak = threadIdx.x & 15;
-    const int bk = threadIdx.x >> 7, bc = threadIdx.x & 127;
-    const double *pa = MA + (long long)(rb + ar) * lda + ak;
-    const double *pb = M + (long long)bk * ld + cb + bc;
-    unsigned amask = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) amask |= (rb + ar + 32 * i < R.r1) ? (1u << i) : 0u;
-    const bool bcol_ok = cb + bc < R.c1;
-    double *sa = smem + ar * BA_LD + ak;
-    double *sb = smem + BM * BA_LD + bk * BB_LD + bc;
-    auto load_stage = [&](int stg, int kb) {
-        const bool ka = kb + ak < R.k1;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool ok = ka && ((amask >> i) & 1u);
-            cp_async8(sa + stg * STAGE_DOUBLES + i * 32 * BA_LD, ok ? pa + (long long)i * 32 * lda + kb : M, ok);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool ok = bcol_ok && (kb + bk + 4 * i < R.k1);
-            cp_async8(sb + stg * STAGE_DOUBLES + i * 4 * BB_LD, ok ? pb + (long long)(kb + 4 * i) * ld : M, ok);
-        }
-    };
-#pragma unroll
-    for (int st = 0; st < STG - 1; ++st) {
-        if (st < nk) load_stage(st, R.k0 + st * BK);
-        cp_async_commit();
-    }
-    for (int kt = 0; kt < nk; ++kt) {
-        cp_async_wait<STG - 2>();
-        __syncthreads();
-        const int nxt = kt + STG - 1;
-        if (nxt < nk) load_stage(nxt % STG, R.k0 + nxt * BK);
-        cp_async_commit();
-        const double *As = smem + (kt % STG) * STAGE_DOUBLES;
-        const double *Bs = As + BM * BA_LD;
-#pragma unroll
-        for (int k4 = 0; k4 < BK / 4; ++k4) {
-            double a[4], b[4];
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi) a[mi] = As[(wm * 32 + mi * 8 + g) * BA_LD + k4 * 4 + t4];
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(k4 * 4 + t4) * BB_LD + wn * 32 + ni * 8 + g];
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-        }
-    }
-    cp_async_wait<0>();
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {
-        const int r = rb + wm * 32 + mi * 8 + g;
-        if (r >= R.r1) continue;
-        double *row = M + (long long)r * ld;
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int c0 = cb + wn * 32 + ni * 8 + 2 * t4;
-            if (c0 < R.c1 && owned_col(ko, c0, F.f)) row[c0] = acc[mi][ni][0];
-            if (c0 + 1 < R.c1 && owned_col(ko, c0 + 1, F.f)) row[c0 + 1] = acc[mi][ni][1];
-        }
-    }
-}
-
-int update_tile_m(int gemm_path) { return gemm_path == 1 ? FT : (gemm_path == 2 ? BM : TM); }
-int update_tile_n(int gemm_path) { return gemm_path == 1 ? FT : (gemm_path == 2 ? BN : TN); }
+int update_tile_m(int gemm_path) { return gemm_path == 1 ? FT : TM; }
+int update_tile_n(int gemm_path) { return gemm_path == 1 ? FT : TN; }
 int update_tile_k() { return TK; }
 
 void init_kernel_attributes() {
@@ -1166,15 +935,10 @@ void init_kernel_attributes() {
                          (int)((size_t)TSTG * TSTAGE_DOUBLES * sizeof(double)));
     cudaFuncSetAttribute(update_dmma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)((size_t)TSTG * TSTAGE_DOUBLES * sizeof(double)));
-    cudaFuncSetAttribute(update_dmma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)((size_t)TSTG * TSTAGE_DOUBLES * sizeof(double)));
     cudaFuncSetAttribute(update_dmma_tmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)((size_t)TMS * TM_STAGE_BYTES));
     cudaFuncSetAttribute(update_dmma_tmap_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                          (int)cudaSharedmemCarveoutMaxShared);   // two 97 KB CTAs per SM
-
-    cudaFuncSetAttribute(update_dmma_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)((size_t)STG * STAGE_DOUBLES * sizeof(double)));
 }
 
 void launch_update(const LaunchCtx &c, const int *ids, int nfb, int j, int mode, int max_tiles, int split) {
@@ -1182,13 +946,6 @@ void launch_update(const LaunchCtx &c, const int *ids, int nfb, int j, int mode,
     dim3 grid(max_tiles, nfb, c.nbatch);
     if (c.gemm_path == 1) {
         update_dfma_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split, c.ko);
-    } else if (c.gemm_path == 2) {
-        const size_t smem = (size_t)STG * STAGE_DOUBLES * sizeof(double);
-        update_dmma_big_kernel<<<grid, 512, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split, c.ko);
-    } else if (c.gemm_path == 3) {
-        const size_t smem = (size_t)TSTG * TSTAGE_DOUBLES * sizeof(double);
-        update_dmma_tma_kernel<<<grid, TMA_THREADS, smem, c.stream>>>(c.pool, c.pool_stride, c.fronts, ids, j, mode, split,
-                                                                     c.ko);
     } else {
         const size_t smem = (size_t)TSTG * TSTAGE_DOUBLES * sizeof(double);
         if (c.tile_m == 64)
@@ -1299,16 +1056,14 @@ template <int WPR>
 __global__ void __launch_bounds__(256)
 assemble_kernel(double *pool, long long pool_stride, const DFront *fronts, const int *ids, const long long *row_base,
                 const long long *row_ptr, const int *row_child, const int *row_crow, const int *__restrict__ rel,
-                const long long *rel_off) {
+                const long long *rel_off, const int *__restrict__ child_split) {
     pdl_enter();
     const int pid = ids[blockIdx.y];
     const DFront P = fronts[pid];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a = blockIdx.x * (8 / WPR) + warp / WPR;
     if (a >= P.f) return;
-    const int part = warp % WPR;
-    const int q = (P.f + WPR - 1) / WPR;                  // parent columns [part*q, part*q + q) belong to this warp
-    const int c_lo = part * q, c_hi = min(P.f, c_lo + q);
+    const int part = warp % WPR;                          // this warp's share of the parent's columns (see child_split)
     double *base = pool + (long long)blockIdx.z * pool_stride;
     double *prow = base + P.off + (long long)a * P.ld;
     const long long r = row_base[pid] + a;
@@ -1319,13 +1074,13 @@ assemble_kernel(double *pool, long long pool_stride, const DFront *fronts, const
         const double *crow = base + C.off + (long long)(C.k + row_crow[e]) * C.ld + C.k;
         const int *rl = rel + rel_off[cid];
         int j0 = 0, j1 = m;
-        if (WPR > 1) {                                    // first child column mapped at or beyond c_lo / c_hi
-            int lo = 0, hi = m;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (rl[mid] < c_lo) lo = mid + 1; else hi = mid; }
-            j0 = lo;
-            hi = m;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (rl[mid] < c_hi) lo = mid + 1; else hi = mid; }
-            j1 = lo;
+        if (WPR > 1) {
+            // first child column mapped at or beyond each quarter of the parent's columns: the same for every row of
+            // this child, so the host tabulates it (a pair of binary searches here cost ~20 dependent loads per
+            // contribution, most of this kernel's time at the top of the tree)
+            const int *sp = child_split + (long long)cid * (WPR - 1);
+            j0 = part == 0 ? 0 : sp[part - 1];
+            j1 = part == WPR - 1 ? m : sp[part];
         }
         int j = j0 + lane;
         for (; j + 96 < j1; j += 128) {                   // four gathers in flight per lane
@@ -1349,92 +1104,114 @@ assemble_kernel(double *pool, long long pool_stride, const DFront *fronts, const
     }
 }
 
+bool assemble_splits_rows(int nparents, int nbatch, int max_f) {
+    return (long long)nparents * nbatch * ((max_f + 7) / 8) < 4 * 148;
+}
+
 void launch_assemble(const LaunchCtx &c, const int *ids, int nparents, int max_f, const long long *row_base,
                      const long long *row_ptr, const int *row_child, const int *row_crow, const int *rel,
-                     const long long *rel_off) {
+                     const long long *rel_off, const int *child_split) {
     if (nparents <= 0 || max_f <= 0) return;
     // few, large parents: four warps per row
-    if ((long long)nparents * c.nbatch * ((max_f + 7) / 8) < 4 * 148) {
+    if (child_split && assemble_splits_rows(nparents, c.nbatch, max_f)) {
         dim3 grid((max_f + 1) / 2, nparents, c.nbatch);
-        launch_chain(assemble_kernel<4>, grid, dim3(256), 0, c.stream, c.pool, c.pool_stride, c.fronts, ids, row_base, row_ptr,
-                     row_child, row_crow, rel, rel_off);
+        launch_chain(assemble_kernel<ASM_WPR>, grid, dim3(256), 0, c.stream, c.pool, c.pool_stride, c.fronts, ids, row_base,
+                     row_ptr, row_child, row_crow, rel, rel_off, child_split);
     } else {
         dim3 grid((max_f + 7) / 8, nparents, c.nbatch);
         launch_chain(assemble_kernel<1>, grid, dim3(256), 0, c.stream, c.pool, c.pool_stride, c.fronts, ids, row_base, row_ptr,
-                     row_child, row_crow, rel, rel_off);
+                     row_child, row_crow, rel, rel_off, child_split);
     }
 }
 
 // =====================================================================================================
-// phase 2 (reference ngt.hpp:362-431): for every a of a group, eliminate the rest of the group.
-// Task front (order ng+1): rows/cols 0..ng-2 = group minus a, row ng-1 = a, column ng = all mass into the
-// other group (collapsed), column ng+1 = tau.  Eliminating its ng-1 pivots with the ordinary front kernels
-// leaves 1-P'_aa in (ng-1, ng) and tau'_a in (ng-1, ng+1).
+// phase 2 (reference ngt.hpp:362-431): for every a of a group, 1-P'_aa and tau'_a after the rest of the group is
+// eliminated.  The reference repeats a full elimination per a (O(|A|^4) in all).  Eliminations commute, so the
+// per-a results are the leaves of a binary tree of eliminations instead: a tree node holds the chain reduced to
+// (kept set S) + (the other group collapsed into one absorbing column); its two children eliminate one half of S each
+// and keep the other.  Every a is still obtained by eliminating group \ {a} -- only the order differs from the
+// reference's and the shared prefixes are computed once: 4/3 |A|^3 flops per group, log2|A| levels of fronts.
+//
+// A phase-2 front (order npk + 1): pivots = parent's kept members that this task drops, then the kept members T, then
+// the collapsed column; column f carries tau.  After its elimination rows/cols k.. are the chain on T: the source of
+// its two children (or, when |T| = 1, the result: 1-P'_aa = M[k][k+1], tau'_a = M[k][f]).
 // =====================================================================================================
+__device__ __forceinline__ int p2_parent_index(const P2Task &t, int l) {
+    const int k = t.npk - t.t_len;                 // dropped members come first
+    if (l < k) return t.t_off == 0 ? t.t_len + l : l;
+    return t.t_off + (l - k);
+}
+
 __global__ void __launch_bounds__(256)
-phase2_gather_kernel(const double *pool, long long pool_stride, DFront root, int g0, int ng, int o0, int no,
-                     double *p2pool, long long p2_stride, const DFront *p2fronts, int task0, int rank, int nranks) {
-    const int t = blockIdx.y;            // task within the group = index of a
-    if (nranks > 1 && (t % nranks) != rank) return;
-    const int lr = blockIdx.x;           // local row of the task front (0..ng-1)
-    const DFront T = p2fronts[task0 + t];
-    const double *R = pool + (long long)blockIdx.z * pool_stride + root.off;
-    double *M = p2pool + (long long)blockIdx.z * p2_stride + T.off;
-    // local index -> group member: members other than a keep root order, a goes last
-    const int gr = (lr == ng - 1) ? t : (lr < t ? lr : lr + 1);
-    const double *src = R + (long long)(g0 + gr) * root.ld;
-    double *dst = M + (long long)lr * T.ld;
-    for (int lc = threadIdx.x; lc < ng; lc += 256) {
-        const int gc = (lc == ng - 1) ? t : (lc < t ? lc : lc + 1);
-        dst[lc] = (lc == lr) ? 0.0 : src[g0 + gc];
+phase2_gather_kernel(const double *pool, long long pool_stride, DFront root, double *p2pool, long long p2_stride,
+                     const DFront *p2fronts, const P2Task *tasks, int task0) {
+    const int tid = task0 + blockIdx.y;
+    const P2Task t = tasks[tid];
+    const DFront D = p2fronts[tid];
+    const int lr = blockIdx.x;                     // row of the new front
+    const int fD = t.npk + 1;                      // members + the collapsed column
+    if (lr >= fD) return;
+    double *M = p2pool + (long long)blockIdx.z * p2_stride + D.off;
+    double *dst = M + (long long)lr * D.ld;
+    if (lr == fD - 1) {                            // the collapsed node is never a pivot: a zero row
+        for (int lc = threadIdx.x; lc <= fD; lc += 256) dst[lc] = 0.0;
+        return;
     }
-    // mass into the other group, summed in a fixed order by warp 0
+    const int pi = p2_parent_index(t, lr);
+    const double *src;
+    int col0, ccol, tcol;                          // first member column, collapsed column, tau column of the source
+    if (t.src < 0) {
+        src = pool + (long long)blockIdx.z * pool_stride + root.off + (long long)(t.src_k + pi) * root.ld;
+        col0 = t.src_k; ccol = -1; tcol = root.f;
+    } else {
+        const DFront S = p2fronts[t.src];
+        src = p2pool + (long long)blockIdx.z * p2_stride + S.off + (long long)(t.src_k + pi) * S.ld;
+        col0 = t.src_k; ccol = t.src_k + t.npk; tcol = S.f;
+    }
+    for (int lc = threadIdx.x; lc < fD - 1; lc += 256)
+        dst[lc] = (lc == lr) ? 0.0 : src[col0 + p2_parent_index(t, lc)];
     if (threadIdx.x < 32) {
         double s = 0.0;
-        for (int c = threadIdx.x; c < no; c += 32) s += src[o0 + c];
-        s = warp_sum(s);
+        if (ccol < 0) {                            // root source: mass into the other group, fixed summation order
+            for (int c = threadIdx.x; c < t.no; c += 32) s += src[t.o0 + c];
+            s = warp_sum(s);
+        } else {
+            s = src[ccol];
+        }
         if (threadIdx.x == 0) {
-            dst[ng] = s;
-            dst[ng + 1] = src[root.f];
+            dst[fD - 1] = s;
+            dst[fD] = src[tcol];
         }
     }
-    // the collapsed "other" node is row ng of the task front: never read (it is not a pivot), keep zero
-    if (lr == 0)
-        for (int lc = threadIdx.x; lc < ng + 2; lc += 256) M[(long long)ng * T.ld + lc] = 0.0;
 }
 
-void launch_phase2_gather(const LaunchCtx &c, DFront root, int g0, int ng, int o0, int no, double *p2pool,
-                          long long p2_stride, const DFront *p2fronts, int task0, int ntask, int rank, int nranks) {
+void launch_phase2_gather(const LaunchCtx &c, DFront root, double *p2pool, long long p2_stride, const DFront *p2fronts,
+                          const P2Task *tasks, int task0, int ntask, int max_f) {
     if (ntask <= 0) return;
-    dim3 grid(ng, ntask, c.nbatch);
-    phase2_gather_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, root, g0, ng, o0, no, p2pool, p2_stride,
-                                                     p2fronts, task0, rank, nranks);
+    dim3 grid(max_f, ntask, c.nbatch);
+    phase2_gather_kernel<<<grid, 256, 0, c.stream>>>(c.pool, c.pool_stride, root, p2pool, p2_stride, p2fronts, tasks, task0);
 }
 
-__global__ void phase2_collect_kernel(const double *p2pool, long long p2_stride, const DFront *p2fronts, int task0,
-                                      int ntask, int ng, double *om, double *tau, int out_stride, int out_off,
-                                      int rank, int nranks) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntask) return;
+// leaves of the tree: front `leaf_front[i]` kept exactly one member, whose result goes to slot leaf_out[i]
+__global__ void phase2_collect_kernel(const double *p2pool, long long p2_stride, const DFront *p2fronts,
+                                      const int *leaf_front, const int *leaf_out, int nleaf, double *om, double *tau,
+                                      int out_stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nleaf) return;
     const long long b = blockIdx.y;
-    double o = 0.0, tt = 0.0;
-    if (nranks <= 1 || (t % nranks) == rank) {
-        const DFront T = p2fronts[task0 + t];
-        const double *M = p2pool + b * p2_stride + T.off;
-        o = M[(long long)(ng - 1) * T.ld + ng];
-        tt = M[(long long)(ng - 1) * T.ld + ng + 1];
-    }
-    om[b * out_stride + out_off + t] = o;
-    tau[b * out_stride + out_off + t] = tt;
+    const DFront T = p2fronts[leaf_front[i]];
+    const double *M = p2pool + b * p2_stride + T.off;
+    om[b * out_stride + leaf_out[i]] = M[(long long)T.k * T.ld + T.k + 1];
+    tau[b * out_stride + leaf_out[i]] = M[(long long)T.k * T.ld + T.f];
 }
 
 void launch_phase2_collect(const LaunchCtx &c, const double *p2pool, long long p2_stride, const DFront *p2fronts,
-                           int task0, int ntask, int ng, double *om, double *tau, int out_stride, int out_off,
-                           int rank, int nranks) {
-    if (ntask <= 0) return;
-    dim3 grid((ntask + 127) / 128, c.nbatch);
-    phase2_collect_kernel<<<grid, 128, 0, c.stream>>>(p2pool, p2_stride, p2fronts, task0, ntask, ng, om, tau,
-                                                     out_stride, out_off, rank, nranks);
+                           const int *leaf_front, const int *leaf_out, int nleaf, double *om, double *tau,
+                           int out_stride) {
+    if (nleaf <= 0) return;
+    dim3 grid((nleaf + 127) / 128, c.nbatch);
+    phase2_collect_kernel<<<grid, 128, 0, c.stream>>>(p2pool, p2_stride, p2fronts, leaf_front, leaf_out, nleaf, om, tau,
+                                                     out_stride);
 }
 
 // =====================================================================================================

@@ -16,9 +16,16 @@
 //     Schur update:          P_RR += P_RX U' ,  tau_R += P_RX tau'_X    (update kernels, FP64 DMMA)
 #pragma once
 #include <cstdint>
+#include <stdexcept>
+#include <string>
 #include <cuda_runtime.h>
 
 namespace ngt {
+
+// thrown by the launchers when the runtime rejects a launch (mapped to NGT_E_CUDA at the C ABI)
+struct LaunchFailure : std::runtime_error {
+    explicit LaunchFailure(const std::string &m) : std::runtime_error(m) {}
+};
 
 #ifndef NGT_NB_OUTER
 #define NGT_NB_OUTER 256
@@ -103,7 +110,7 @@ struct LaunchCtx {
     int maxchunks;
     int *errflag;             // device int
     cudaStream_t stream;
-    int gemm_path;            // 0 DMMA, 1 DFMA
+    int gemm_path;            // 0 DMMA (FP64 tensor cores), 1 scalar DFMA (cross-check)
     KOpt ko;                  // {0,0,0,FUSE_COLS} outside the multi-GPU dense path
     int panel_cluster = 0;      // 1: panel kernel runs as clusters of PANEL_CLUSTER CTAs per front and includes the row
                                 // sums and the row panel (no rowsum / rowpanel launch for this step)
@@ -144,22 +151,33 @@ void launch_ingest_dense(double *pool, long long pool_stride, int nbatch, const 
                          int nI, DFront f0, DFront root, double *tau0, int *errflag, cudaStream_t s);
 
 // ---- assembly: child update blocks (+ delta-tau column) are added into their parents -----------------------
-// ids: parents of one tree level; child_ptr/child_ids: CSR of children per front; inv/inv_off: per child, parent local
-// index -> child update index or -1
+// ids: parents of one tree level; row_base / row_ptr / row_child / row_crow: per parent row, the (child, child update
+// row) pairs that add into it; rel / rel_off: per child, child update index -> parent local index (ascending).
+// Levels with a few large parents run ASM_WPR warps per parent row, each owning one ASM_WPR-th of the parent's columns
+// (assemble_splits_rows tells which); child_split[c * (ASM_WPR-1) + i] = first update index of child c mapped at or
+// beyond parent column (i+1) * ceil(f_parent / ASM_WPR), tabulated by the host for the children of such parents.
+constexpr int ASM_WPR = 4;
+bool assemble_splits_rows(int nparents, int nbatch, int max_f);
 void launch_assemble(const LaunchCtx &c, const int *ids, int nparents, int max_f, const long long *row_base,
                      const long long *row_ptr, const int *row_child, const int *row_crow, const int *rel,
-                     const long long *rel_off);
+                     const long long *rel_off, const int *child_split);
 
-// ---- phase 2: build one front per a in the group from the reduced root block -----------------------
-// group = [g0, g0+ng) rows of the root, other = the remaining root rows.  Task t (a = g0 + t) gets a front of
-// order ng+1: pivots = group minus a (root order), then a, then the collapsed "other" column; tau in column ng+1.
-void launch_phase2_gather(const LaunchCtx &c, DFront root, int g0, int ng, int o0, int no,
-                          double *p2pool, long long p2_stride, const DFront *p2fronts, int task0, int ntask,
-                          int rank, int nranks);
-// read 1-P'_aa (row ng-1, col ng) and tau'_a (row ng-1, col ng+1) of every task front
+// ---- phase 2: a binary tree of eliminations per group (see kernels.cu) -------------------------------
+struct P2Task {       // one phase-2 front = "parent's kept members minus T are eliminated, T is kept"
+    int src;          // source front (index into the phase-2 front array), or -1: the reduced root block
+    int src_k;        // first kept row / column in the source (= its pivot count; root: first row of the group)
+    int npk;          // members the source kept (the new front has order npk + 1: + the collapsed other group)
+    int t_off, t_len; // T = source's kept members [t_off, t_off + t_len): a prefix or a suffix
+    int o0, no;       // root source only: columns [o0, o0 + no) of the other group collapse into one
+    int pad;
+};
+// build the fronts task0 .. task0+ntask-1 (one tree level) from their sources; max_f = largest new order
+void launch_phase2_gather(const LaunchCtx &c, DFront root, double *p2pool, long long p2_stride, const DFront *p2fronts,
+                          const P2Task *tasks, int task0, int ntask, int max_f);
+// read 1-P'_aa and tau'_a from the fronts that kept a single member
 void launch_phase2_collect(const LaunchCtx &c, const double *p2pool, long long p2_stride, const DFront *p2fronts,
-                           int task0, int ntask, int ng, double *om, double *tau, int out_stride, int out_off,
-                           int rank, int nranks);
+                           const int *leaf_front, const int *leaf_out, int nleaf, double *om, double *tau,
+                           int out_stride);
 
 // ---- multi-GPU dense path helpers (see kernels.cu) --------------------------------------------------------
 void launch_dist_rowsum(const double *M, int ld, int f, int J, int JE, KOpt ko, double *out, cudaStream_t s);

@@ -93,8 +93,12 @@ class GraphReduction(object):
         self._Bids = [self._node2id[b] for b in self.B]
         self._Alist, self._Blist = list(self.A), list(self.B)
         self._h = _capi.Handle.from_coo(len(self._nodes), src, dst, k, self._Aids, self._Bids, **self._opt)
-        ids = [self._node2id[x] for x in self._Alist + self._Blist]
-        self._h.set_weights(ids, [self.weights[x] for x in self._Alist + self._Blist])
+        # the reference reads weights lazily, per group and only in the getter that needs them (_kmc_rates.py:168-172):
+        # a plain dict that covers A alone is enough for get_rate_AB().  Push what exists; missing entries surface as
+        # KeyError in the getter that asks for them, as in the reference.
+        known = [x for x in self._Alist + self._Blist if isinstance(self.weights, defaultdict) or x in self.weights]
+        if known:
+            self._h.set_weights([self._node2id[x] for x in known], [self.weights[x] for x in known])
 
     @property
     def _tau0(self):
@@ -132,10 +136,14 @@ class GraphReduction(object):
 
     # ---- the reference's public methods --------------------------------------------------------------
     def compute_rates(self):
-        """do the computation to compute the rates"""
+        """Run phase 1 and phase 2 on the GPU and cache 1-P'_xx and tau'_x of every x in A and B."""
         self._h.compute_rates()
         om, tau = self._h.final()
         for i, x in enumerate(self._Alist + self._Blist):
+            if not om[i] > 0.:
+                # x keeps no edge besides its self loop once the rest of its group is gone
+                # (the reference's check, _kmc_rates.py:227-228)
+                raise Exception("node %s is not connected" % (x,))
             self._final_omPxx[x] = float(om[i])
             self._final_Pxx[x] = 1. - float(om[i])
             self._final_tau[x] = float(tau[i])
@@ -143,13 +151,11 @@ class GraphReduction(object):
         self._graph = None
 
     def get_rate_AB(self):
-        """Return the transition rate from A to B
-
-        This is the inverse mean first passage time averaged over the elements in A"""
+        """k_AB: the weighted mean over a in A of 1 / (mean first-passage time from a into B)."""
         return self._get_final_rate(self._Alist)
 
     def get_rate_BA(self):
-        """Return the transition rate from B to A"""
+        """k_BA: the same average taken over the members of B, for passages into A."""
         return self._get_final_rate(self._Blist)
 
     def _get_final_rate(self, group):
@@ -169,13 +175,8 @@ class GraphReduction(object):
         return rate / sum(self.weights[x] for x in self._Alist)
 
     def get_committor_probabilityAB(self, x):
-        """return the committor probability for node x
-
-        x must be in A or in B. If x is in A return the the probability
-        that a trajectory starting at x gets to B before returning to x.
-        If x is in B return the the probability
-        that a trajectory starting at x gets to A before returning to x.
-        """
+        """1 - P'_xx of an end-point node x after phase 2: for x in A the chance that a walker leaving x arrives in B
+        before it is back at x; for x in B the same with A as the target.  Only defined for members of A or B."""
         if len(self._final_Pxx) == 0:
             raise RuntimeError("you must call compute_rates before calling this function")
         try:
@@ -185,13 +186,12 @@ class GraphReduction(object):
                 raise ValueError("x is not in A or in B.  Use compute_committor_probability() if x is an intermediate")
 
     def compute_committor_probability(self, x):
-        """compute the probability that trajectory starting from x reaches B before it reaches A"""
+        """Committor of a single node: the chance of hitting B before A when starting at x."""
         return self.compute_committor_probabilities([x])[x]
 
     def compute_committor_probabilities(self, nodes):
         """
-        compute the committor probability for each node in nodes: the probability that the trajectory
-        starting from node x reaches B before it reaches A.
+        Committors (probability of reaching B before A) of all `nodes`, as a dict node -> value.
 
         The reference must be asked before compute_rates() because it destroys its graph
         (reference _kmc_rates.py:496-546); here the order does not matter.  Nodes of A ∪ B get

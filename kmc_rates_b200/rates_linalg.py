@@ -74,6 +74,17 @@ class TwoStateRates(object):
 
     def _handle(self, A, B):
         src, dst, k = self._coo
+        # The reference's linear solves treat B (and A, for committors) as absorbing and never read rates out of them
+        # (reference rates_linalg.py:246-285), so a product node may be a pure sink.  The elimination engine wants a
+        # waiting time for every node: kept nodes without an outgoing rate get a self rate, which no result depends on.
+        has_out = np.zeros(len(self._labels), bool)
+        has_out[src] = True
+        sinks = [self._labels[x] for x in list(A) + list(B) if not has_out[self._labels[x]]]
+        if sinks:
+            sinks = np.asarray(sinks, np.int64)
+            src = np.concatenate([src, sinks])
+            dst = np.concatenate([dst, sinks])
+            k = np.concatenate([k, np.ones(sinks.size)])
         return _capi.Handle.from_coo(len(self._labels), src, dst, k, [self._labels[a] for a in A],
                                      [self._labels[b] for b in B], device=self._device)
 
