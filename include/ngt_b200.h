@@ -152,7 +152,8 @@ int ngt_adopt_final_dev(ngt_handle h);
  *     ngt_dist_panel(h, J, &p, &n)      broadcast the n doubles at p from the owner
  *     ngt_dist_apply(h, J)              every rank
  * and finally ngt_dist_root (all-reduce(sum) its buffer), ngt_dist_finish, then ngt_phase_two / getters as usual.
- * The collectives are the caller's (NCCL through torch.distributed in kmc_rates_b200/distributed.py). */
+ * These staged calls are synchronous and leave the collectives to the caller (used by the emulated-rank tests);
+ * ngt_dist_phase_one below runs the same stages from C++ with NCCL and no host synchronisation between blocks. */
 int ngt_dist_begin(ngt_handle h, int32_t rank, int32_t world);
 int ngt_dist_info(ngt_handle h, int64_t *n_pivots, int64_t *block);
 int ngt_dist_rowsum(ngt_handle h, int64_t J, double **dptr, int64_t *ndoubles);
@@ -161,6 +162,25 @@ int ngt_dist_panel(ngt_handle h, int64_t J, double **dptr, int64_t *ndoubles);
 int ngt_dist_apply(ngt_handle h, int64_t J);
 int ngt_dist_root(ngt_handle h, double **dptr, int64_t *ndoubles);
 int ngt_dist_finish(ngt_handle h);
+
+/* ---- multi-GPU, driven from C++ with NCCL on the engine's own streams --------------------------------------
+ * One communicator per process and GPU.  NCCL is bound at run time (dlopen of the libnccl.so.2 the host process
+ * already uses); the 128-byte unique id is made on one rank (ngt_comm_unique_id) and handed to the others by
+ * whatever the host has (torch.distributed, MPI, a file).  ngt_comm_create is collective over the ranks.
+ *   ngt_dist_phase_one      phase 1 of ONE dense network over the ranks (every rank holds a handle created from the
+ *                           same rate matrix): the whole block loop -- row-sum all-reduce, panel factorisation on
+ *                           the owner, panel broadcast, trailing update of the own columns with look-ahead -- is
+ *                           enqueued without a host synchronisation between blocks.  Then ngt_phase_two / getters.
+ *   ngt_phase_two_sharded   after phase 1 on every rank (replicated, or rank 0's reduced block broadcast when
+ *                           broadcast_root != 0): this rank's share of phase 2, one in-place all-reduce of the
+ *                           (1-P'_aa, tau'_a) vectors, rates available on every rank.
+ * ms_device (may be NULL) receives the device time of the call from CUDA events on the engine's main stream. */
+typedef struct ngt_comm_s *ngt_comm;
+int ngt_comm_unique_id(uint8_t id[128]);
+int ngt_comm_create(int32_t device, const uint8_t id[128], int32_t rank, int32_t world, ngt_comm *out);
+void ngt_comm_destroy(ngt_comm c);
+int ngt_dist_phase_one(ngt_handle h, ngt_comm c, double *ms_device);
+int ngt_phase_two_sharded(ngt_handle h, ngt_comm c, int32_t broadcast_root, double *ms_device);
 
 /* Device buffers of destroyed handles are cached per process for reuse by later handles (cudaMalloc/cudaFree of the
  * front pools cost ~0.1 s), and so are the host temporaries of the sparse analysis (up to 1 GB; their first-touch page

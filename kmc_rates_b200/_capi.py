@@ -104,6 +104,10 @@ def lib():
         "ngt_dist_apply": [H, i64],
         "ngt_dist_root": [H, ctypes.POINTER(vp), _i64p],
         "ngt_dist_finish": [H],
+        "ngt_comm_unique_id": [ctypes.POINTER(ctypes.c_uint8)],
+        "ngt_comm_create": [ctypes.c_int32, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int32, ctypes.c_int32, HP],
+        "ngt_dist_phase_one": [H, H, _f64p],
+        "ngt_phase_two_sharded": [H, H, ctypes.c_int32, _f64p],
     }
     for name, args in sig.items():
         f = getattr(L, name)
@@ -111,6 +115,8 @@ def lib():
         f.restype = ctypes.c_int
     L.ngt_destroy.argtypes = [H]
     L.ngt_destroy.restype = None
+    L.ngt_comm_destroy.argtypes = [H]
+    L.ngt_comm_destroy.restype = None
     L.ngt_trim_device_cache.argtypes = []
     L.ngt_trim_device_cache.restype = None
     L.ngt_last_error.restype = ctypes.c_char_p
@@ -126,6 +132,7 @@ EXPORTED_SYMBOLS = [
     "ngt_get_stats", "ngt_timed_steps", "ngt_profile_schur", "ngt_batch_create", "ngt_batch_create_dense", "ngt_batch_create_dense_dev", "ngt_batch_get_rates",
     "ngt_reduced_block_dev", "ngt_phase_two_shard", "ngt_set_final", "ngt_final_dev", "ngt_adopt_final_dev", "ngt_dist_begin", "ngt_dist_info", "ngt_dist_rowsum",
     "ngt_dist_factor", "ngt_dist_panel", "ngt_dist_apply", "ngt_dist_root", "ngt_dist_finish", "ngt_trim_device_cache",
+    "ngt_comm_unique_id", "ngt_comm_create", "ngt_comm_destroy", "ngt_dist_phase_one", "ngt_phase_two_sharded",
     "ngt_last_error",
     "ngt_version",
 ]
@@ -150,6 +157,49 @@ def _ids(seq):
 
 def _is_torch_cuda(x):
     return hasattr(x, "data_ptr") and hasattr(x, "is_cuda") and x.is_cuda
+
+
+class Comm(object):
+    """One NCCL communicator per process and GPU, created by the library itself (include/ngt_b200.h, ngt_comm_*).
+
+    `exchange(id_bytes_or_None) -> id_bytes` hands rank 0's 128-byte unique id to the other ranks; from_torch() does it
+    with torch.distributed (any backend), which is only plumbing here -- the collectives of the sharded paths are NCCL
+    calls made by the C++ engine on its own streams."""
+
+    def __init__(self, device, rank, world, exchange):
+        self.c = ctypes.c_void_p()
+        self.rank, self.world, self.device = int(rank), int(world), int(device)
+        buf = (ctypes.c_uint8 * 128)()
+        if rank == 0:
+            check(lib().ngt_comm_unique_id(buf))
+        got = exchange(bytes(buf) if rank == 0 else None)
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(got)
+        check(lib().ngt_comm_create(self.device, buf, self.rank, self.world, ctypes.byref(self.c)))
+
+    @classmethod
+    def from_torch(cls, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if device is None:
+            device = torch.cuda.current_device()
+
+        def exchange(b):
+            box = [b]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            return box[0]
+        return cls(device, rank, world, exchange)
+
+    def close(self):
+        if self.c:
+            lib().ngt_comm_destroy(self.c)
+            self.c = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Handle(object):
@@ -382,6 +432,19 @@ class Handle(object):
 
     def adopt_final_dev(self):
         check(lib().ngt_adopt_final_dev(self.h))
+
+    def dist_phase_one(self, comm):
+        """phase 1 of one dense network over the ranks of `comm` (C++ block loop, NCCL on the engine's streams);
+        returns the device time in ms"""
+        ms = ctypes.c_double()
+        check(lib().ngt_dist_phase_one(self.h, comm.c, ctypes.byref(ms)))
+        return ms.value
+
+    def phase_two_sharded(self, comm, broadcast_root=False):
+        """this rank's share of phase 2 + in-place NCCL all-reduce of the results; returns the device time in ms"""
+        ms = ctypes.c_double()
+        check(lib().ngt_phase_two_sharded(self.h, comm.c, 1 if broadcast_root else 0, ctypes.byref(ms)))
+        return ms.value
 
     def reduced_block_dev(self):
         p = ctypes.c_void_p()

@@ -12,6 +12,7 @@
 #include "symbolic.h"
 
 #include <cuda.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <chrono>
@@ -143,6 +144,68 @@ struct DevBuf {
         n = cap = 0;
     }
     ~DevBuf() { release(); }
+};
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// NCCL, bound at run time.  The library takes no link-time dependency on it: the host process (torch, MPI, ...) has
+// normally loaded libnccl.so.2 already and dlopen returns that copy.  Only the handful of entry points the sharded
+// paths need are declared (ABI stable since NCCL 2.0).
+// ---------------------------------------------------------------------------------------------------------------
+struct NcclApi {
+    typedef struct ncclComm *comm_t;
+    struct unique_id { char internal[128]; };
+    static constexpr int F64 = 8, SUM = 0;
+    int (*GetUniqueId)(unique_id *) = nullptr;
+    int (*CommInitRank)(comm_t *, int, unique_id, int) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    void *lib = nullptr;
+    std::string why;
+
+    static NcclApi &get() {
+        static NcclApi api = [] {
+            NcclApi a;
+            const char *names[] = {"libnccl.so.2", "libnccl.so"};
+            for (const char *nm : names) {
+                a.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+                if (a.lib) break;
+            }
+            if (!a.lib) { a.why = std::string("libnccl.so.2 not found: ") + dlerror(); return a; }
+            auto sym = [&](const char *n) { void *p = dlsym(a.lib, n); if (!p) a.why = std::string("NCCL symbol missing: ") + n; return p; };
+            a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
+            a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
+            a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+            a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
+            a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(sym("ncclBroadcast"));
+            a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
+            a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
+            a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
+            a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+            return a;
+        }();
+        if (!api.lib || !api.why.empty()) throw CudaError("NCCL unavailable: " + api.why);
+        return api;
+    }
+};
+#define NK(call)                                                                                         \
+    do {                                                                                                 \
+        int r_ = (call);                                                                                 \
+        if (r_ != 0)                                                                                     \
+            throw CudaError(std::string(#call) + ": " + NcclApi::get().GetErrorString(r_) + " (" __FILE__ ":" + \
+                            std::to_string(__LINE__) + ")");                                             \
+    } while (0)
+
+// one communicator per process and GPU; the collectives run on the engine's own streams
+struct Comm {
+    NcclApi::comm_t comm = nullptr;
+    int rank = 0, world = 1, device = 0;
+    ~Comm() { if (comm) NcclApi::get().CommDestroy(comm); }
 };
 
 using ngt::DFront;
@@ -961,8 +1024,10 @@ struct Engine {
 
     // ---------------------------------------------------------------------------------------------
     // Single dense network over several GPUs: 1-D block-cyclic columns (block = NB_OUTER), panel broadcast.
-    // The collectives themselves are issued by the host language over torch.distributed / NCCL on the device
-    // pointers these methods hand out (kmc_rates_b200/distributed.py); each method is synchronous on return.
+    // Two drivers share the stages below: (1) dist_phase_one(comm) enqueues the whole block loop on the engine's
+    // streams with NCCL called directly -- no host synchronisation between blocks; (2) the staged C ABI
+    // (ngt_dist_rowsum / factor / panel / apply), synchronous per call, for callers that bring their own
+    // collectives (the emulated-rank tests, kmc_rates_b200/distributed.py::dense_phase_one_emulated).
     // ---------------------------------------------------------------------------------------------
     int dist_G = 0, dist_g = 0;
     static constexpr int LD_PAN = ngt::NB_OUTER + 8;
@@ -970,7 +1035,10 @@ struct Engine {
     DevBuf<double> d_pan, d_spart, d_tauglob, d_rootc;
     size_t pan_stride = 0;
     double *pan_buf(int J) { return d_pan.p + (size_t)((J / ngt::NB_OUTER) & 1) * pan_stride; }
-    DevBuf<DFront> d_dfronts;   // [0] panel front, [1] big matrix with the panel as A operand
+    // descriptors of every outer block, uploaded once: [2 blk] the rectangular panel front, [2 blk + 1] the big matrix
+    // with that block's panel buffer as the A operand of its Schur updates
+    DevBuf<DFront> d_dfronts;
+    std::vector<DFront> h_dfronts;
     DevBuf<int> d_dids;
 
     ngt::KOpt own() const { return ngt::KOpt{dist_G, dist_g, 0, 0}; }
@@ -989,8 +1057,28 @@ struct Engine {
         d_spart.alloc(ngt::NB_OUTER);
         d_tauglob.alloc((size_t)n);
         d_rootc.alloc((size_t)m * m);
-        d_dfronts.alloc(3);            // [0] panel front, [1]/[2] big matrix with panel buffer 0/1 as A operand
-        d_dids.upload(std::vector<int>{0, 1, 2});
+        const int nblk = (int)((S.nI + ngt::NB_OUTER - 1) / ngt::NB_OUTER);
+        h_dfronts.assign((size_t)2 * nblk, DFront{});
+        std::vector<int> iota((size_t)2 * nblk);
+        for (int b = 0; b < nblk; ++b) {
+            const int J = b * ngt::NB_OUTER, kb = block_end(J) - J, fr = F0.f - J;
+            double *pan = pan_buf(J) + W_DOUBLES;
+            DFront &P = h_dfronts[2 * b];
+            P.off = pan - d_pool.p;          // the kernels address fronts relative to the pool base
+            P.f = kb + 1;                    // kb block columns + S; column kb+1 is tau
+            P.k = kb;
+            P.ld = LD_PAN;
+            P.parent = -1;
+            P.fr = fr;
+            DFront &B = h_dfronts[2 * b + 1];
+            B.off = F0.off; B.f = F0.f; B.k = F0.k; B.ld = F0.ld; B.parent = -1; B.fr = 0;
+            B.a_ld = LD_PAN;
+            B.a_off = (pan - d_pool.p) - (long long)J * LD_PAN - J;   // A(r, p) = pan[(r - J) * LD_PAN + (p - J)]
+            iota[2 * b] = 2 * b;
+            iota[2 * b + 1] = 2 * b + 1;
+        }
+        d_dfronts.upload(h_dfronts);
+        d_dids.upload(iota);
         d2_pending = false;
         if ((int)(ngt::NB_OUTER / ngt::NB_INNER) > maxfb) {
             // wbuf grows (one W per inner panel of an outer block): a step graph captured earlier has the old pointer
@@ -1015,33 +1103,24 @@ struct Engine {
     int block_end(int J) const { return (int)std::min<int64_t>(J + ngt::NB_OUTER, S.nI); }
 
     // partial mass of the block rows into this rank's columns right of the block -> d_spart (to be all-reduced)
-    double *dist_rowsum(int J) {
-        dist_check(J);
+    void dist_rowsum_enqueue(int J) {
         const ngt::Front &F0 = S.fronts[0];
         const int JE = block_end(J);
         CK(cudaMemsetAsync(d_spart.p, 0, ngt::NB_OUTER * sizeof(double), stream));
         ngt::launch_dist_rowsum(d_pool.p + F0.off, F0.ld, F0.f, J, JE, own(), d_spart.p, stream);
-        CK(cudaStreamSynchronize(stream));
-        return d_spart.p;
+        st.n_launches++;
     }
 
     // owner: build the panel front from its own columns and factor it with the ordinary front kernels
-    void dist_factor(int J) {
-        dist_check(J);
+    void dist_factor_enqueue(int J) {
         const ngt::Front &F0 = S.fronts[0];
         const int JE = block_end(J), kb = JE - J, fr = F0.f - J;
+        const int blk = J / ngt::NB_OUTER;
+        const DFront &P = h_dfronts[2 * blk];
         double *pan = pan_buf(J) + W_DOUBLES;
         ngt::launch_dist_pack(d_pool.p + F0.off, F0.ld, J, kb, fr, pan, LD_PAN, d_spart.p, d_tauglob.p, stream);
-        DFront P{};
-        P.off = pan - d_pool.p;          // the kernels address fronts relative to the pool base
-        P.f = kb + 1;                    // kb block columns + S; column kb+1 is tau
-        P.k = kb;
-        P.ld = LD_PAN;
-        P.parent = -1;
-        P.fr = fr;
-        CK(cudaMemcpyAsync(d_dfronts.p, &P, sizeof(DFront), cudaMemcpyHostToDevice, stream));
         HostBatch hb;
-        hb.ids = {0}; hb.f = {P.f}; hb.k = {P.k}; hb.fr = {fr}; hb.max_k = kb; hb.dev_off = 0;
+        hb.ids = {2 * blk}; hb.f = {P.f}; hb.k = {P.k}; hb.fr = {fr}; hb.max_k = kb; hb.dev_off = 2 * blk;
         ngt::LaunchCtx c = ctx(d_pool.p, pool_stride, d_dfronts.p);
         c.f0 = &P;
         wslot_per_step = true;
@@ -1057,7 +1136,6 @@ struct Engine {
         wslot_per_step = false;
         use_lookahead = la;
         CK(cudaMemcpyAsync(pan_buf(J), d_wbuf.p, W_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice, stream));
-        CK(cudaStreamSynchronize(stream));
     }
 
     // what travels: [W of the block's inner panels | panel front rows J..f-1]
@@ -1070,27 +1148,22 @@ struct Engine {
     // everybody: replay the block's row operations on the own columns, then the trailing update with the panel as A.
     // Look-ahead: only the strips the NEXT block needs (its columns, its rows) are updated on the main stream; the
     // rest of the trailing update runs on the second stream and overlaps the next block's row sums, all-reduce,
-    // panel factorisation and broadcast.  The call returns when the main stream is done.
-    void dist_apply(int J) {
-        dist_check(J);
+    // panel factorisation and broadcast.
+    void dist_apply_enqueue(int J) {
         const ngt::Front &F0 = S.fronts[0];
         const int JE = block_end(J), kb = JE - J, fr = F0.f - J;
-        const int par = (J / ngt::NB_OUTER) & 1;
+        const int blk = J / ngt::NB_OUTER;
         const double *pan = pan_buf(J) + W_DOUBLES;
         CK(cudaMemcpyAsync(d_wbuf.p, pan_buf(J), W_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice, stream));
         ngt::launch_dist_tau(pan, LD_PAN, kb, fr, J, d_tauglob.p, stream);
-        DFront B{};
-        B.off = F0.off; B.f = F0.f; B.k = F0.k; B.ld = F0.ld; B.parent = -1; B.fr = 0;
-        B.a_ld = LD_PAN;
-        B.a_off = (pan - d_pool.p) - (long long)J * LD_PAN - J;   // A(r, p) = pan[(r - J) * LD_PAN + (p - J)]
-        CK(cudaMemcpyAsync(d_dfronts.p + 1 + par, &B, sizeof(DFront), cudaMemcpyHostToDevice, stream));
+        const DFront &B = h_dfronts[2 * blk + 1];
         HostBatch hb;
-        hb.ids = {1 + par}; hb.f = {B.f}; hb.k = {B.k}; hb.max_k = B.k; hb.dev_off = 0;
+        hb.ids = {2 * blk + 1}; hb.f = {B.f}; hb.k = {B.k}; hb.max_k = B.k; hb.dev_off = 0;
         const int tm = ngt::update_tile_m(opt.gemm_path), tn = ngt::update_tile_n(opt.gemm_path);
         ngt::LaunchCtx c = ctx(d_pool.p, pool_stride, d_dfronts.p);
         c.ko = own();
         c.f0 = &B;
-        const int *ids = d_dids.p + 1 + par;
+        const int *ids = d_dids.p + 2 * blk + 1;
         double fl = 0;
         for (int j = J; j < JE; j += ngt::NB_INNER) {
             c.ko.wslot = (j - J) / ngt::NB_INNER;
@@ -1122,16 +1195,12 @@ struct Engine {
             st.n_launches++;
         }
         st.schur_flops += fl / dist_G;   // region flops; a rank performs its 1/G share of the columns
-        CK(cudaStreamSynchronize(stream));
     }
 
-    double *dist_root_contrib() {
-        if (dist_G < 1) throw StateError("ngt_dist_begin has not been called");
+    void dist_root_contrib_enqueue() {
         const ngt::Front &F0 = S.fronts[0];
         if (d2_pending) { CK(cudaStreamWaitEvent(stream, sync_event(1), 0)); d2_pending = false; }
         ngt::launch_dist_root_contrib(d_pool.p + F0.off, F0.ld, F0.f, (int)S.nI, m, own(), d_rootc.p, stream);
-        CK(cudaStreamSynchronize(stream));
-        return d_rootc.p;
     }
 
     void dist_finish() {
@@ -1143,6 +1212,93 @@ struct Engine {
         have_phase1 = true;
         have_phase2 = have_backsub = false;
         last_step_graph = true;   // no per-phase events were recorded for this pass
+    }
+
+    // staged, synchronous variants (C ABI ngt_dist_*)
+    double *dist_rowsum(int J) {
+        dist_check(J);
+        dist_rowsum_enqueue(J);
+        CK(cudaStreamSynchronize(stream));
+        return d_spart.p;
+    }
+    void dist_factor(int J) {
+        dist_check(J);
+        dist_factor_enqueue(J);
+        CK(cudaStreamSynchronize(stream));
+    }
+    void dist_apply(int J) {
+        dist_check(J);
+        dist_apply_enqueue(J);
+        CK(cudaStreamSynchronize(stream));
+    }
+    double *dist_root_contrib() {
+        if (dist_G < 1) throw StateError("ngt_dist_begin has not been called");
+        dist_root_contrib_enqueue();
+        CK(cudaStreamSynchronize(stream));
+        return d_rootc.p;
+    }
+
+    // The whole phase 1 of one dense network over the ranks of `cm`: every stage of every block is enqueued on the
+    // engine's streams, the three collectives per block (row-sum all-reduce, panel broadcast; root all-reduce at the
+    // end) are NCCL calls on the same stream, so the GPU never waits for the host between blocks.
+    // ms (optional): device time of the loop from CUDA events on the main stream.
+    void dist_phase_one(Comm &cm, double *ms) {
+        NcclApi &nc = NcclApi::get();
+        if (cm.device != device) throw InvalidError("communicator and handle live on different devices");
+        dist_begin(cm.rank, cm.world);
+        const int block = ngt::NB_OUTER;
+        CK(cudaEventRecord(ev[0], stream));
+        for (int J = 0; J < (int)S.nI; J += block) {
+            dist_rowsum_enqueue(J);
+            NK(nc.AllReduce(d_spart.p, d_spart.p, (size_t)block, NcclApi::F64, NcclApi::SUM, cm.comm, stream));
+            const int owner = (J / block) % cm.world;
+            if (cm.rank == owner) dist_factor_enqueue(J);
+            double *p = nullptr;
+            int64_t cnt = 0;
+            dist_panel(J, &p, &cnt);
+            NK(nc.Broadcast(p, p, (size_t)cnt, NcclApi::F64, owner, cm.comm, stream));
+            dist_apply_enqueue(J);
+        }
+        dist_root_contrib_enqueue();
+        NK(nc.AllReduce(d_rootc.p, d_rootc.p, (size_t)m * m, NcclApi::F64, NcclApi::SUM, cm.comm, stream));
+        CK(cudaEventRecord(ev[2], stream));
+        CK(cudaGetLastError());
+        dist_finish();
+        if (ms) {
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, ev[0], ev[2]));
+            *ms = t;
+        }
+    }
+
+    // Sharded phase 2 over the ranks of `cm`: optional NCCL broadcast of rank 0's reduced block (so that every rank
+    // reduces bit-identical input), this rank's branches of the elimination tree, one in-place all-reduce(sum) of the
+    // (1-P'_aa, tau'_a) vectors on the engine's stream, then the rates on every rank.
+    void phase_two_sharded(Comm &cm, bool broadcast_root, double *ms) {
+        NcclApi &nc = NcclApi::get();
+        if (!have_phase1) throw StateError("phase_two called before phase_one");
+        if (cm.device != device) throw InvalidError("communicator and handle live on different devices");
+        CK(cudaSetDevice(device));
+        cudaEvent_t e0 = prof_event(), e1 = prof_event();
+        CK(cudaEventRecord(e0, stream));
+        if (broadcast_root && cm.world > 1) {
+            double *blk = d_pool.p + S.fronts[S.root_id].off;
+            for (int b = 0; b < nbatch; ++b)
+                NK(nc.Broadcast(blk + (size_t)b * pool_stride, blk + (size_t)b * pool_stride, (size_t)m * root_ld,
+                                NcclApi::F64, 0, cm.comm, stream));
+        }
+        phase_two_enqueue(cm.rank, cm.world);
+        if (cm.world > 1) {
+            NK(nc.AllReduce(d_om.p, d_om.p, (size_t)nbatch * m, NcclApi::F64, NcclApi::SUM, cm.comm, stream));
+            NK(nc.AllReduce(d_ftau.p, d_ftau.p, (size_t)nbatch * m, NcclApi::F64, NcclApi::SUM, cm.comm, stream));
+        }
+        CK(cudaEventRecord(e1, stream));
+        phase_two_finish(1);      // downloads the merged vectors and forms the rates
+        if (ms) {
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, e0, e1));
+            *ms = t;
+        }
     }
 
     // committors and MFPTs of every eliminated node by back-substitution (top-down over the assembly tree)
@@ -1850,6 +2006,55 @@ int ngt_dist_info(ngt_handle h, int64_t *n_pivots, int64_t *block) {
     return guard([&] {
         *n_pivots = eng(h)->S.nI;
         *block = ngt::NB_OUTER;
+    });
+}
+
+// ---- NCCL communicator + the sharded paths driven from C++ ----------------------------------------------------
+int ngt_comm_unique_id(uint8_t id[128]) {
+    return guard([&] {
+        if (!id) throw InvalidError("null id buffer");
+        NcclApi::unique_id u;
+        NK(NcclApi::get().GetUniqueId(&u));
+        std::memcpy(id, u.internal, 128);
+    });
+}
+
+int ngt_comm_create(int32_t device, const uint8_t id[128], int32_t rank, int32_t world, ngt_comm *out) {
+    return guard([&] {
+        if (!out || !id) throw InvalidError("null pointer");
+        *out = nullptr;
+        if (world < 1 || rank < 0 || rank >= world) throw InvalidError("bad rank / world size");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw CudaError("no CUDA device — kmc_rates_b200 has no CPU fallback");
+        if (device < 0 || device >= ndev) throw InvalidError("device ordinal out of range");
+        CK(cudaSetDevice(device));
+        std::unique_ptr<Comm> c(new Comm());
+        c->rank = rank; c->world = world; c->device = device;
+        NcclApi::unique_id u;
+        std::memcpy(u.internal, id, 128);
+        NK(NcclApi::get().CommInitRank(&c->comm, world, u, rank));
+        *out = reinterpret_cast<ngt_comm>(c.release());
+    });
+}
+
+void ngt_comm_destroy(ngt_comm c) {
+    if (!c) return;
+    Comm *cm = reinterpret_cast<Comm *>(c);
+    cudaSetDevice(cm->device);
+    delete cm;
+}
+
+int ngt_dist_phase_one(ngt_handle h, ngt_comm c, double *ms_device) {
+    return guard([&] {
+        if (!c) throw InvalidError("null communicator");
+        eng(h)->dist_phase_one(*reinterpret_cast<Comm *>(c), ms_device);
+    });
+}
+
+int ngt_phase_two_sharded(ngt_handle h, ngt_comm c, int32_t broadcast_root, double *ms_device) {
+    return guard([&] {
+        if (!c) throw InvalidError("null communicator");
+        eng(h)->phase_two_sharded(*reinterpret_cast<Comm *>(c), broadcast_root != 0, ms_device);
     });
 }
 

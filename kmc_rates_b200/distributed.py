@@ -1,21 +1,29 @@
-"""Multi-GPU plumbing (one process per GPU, torch.distributed; NCCL on GPUs, gloo in the CPU tests).
+"""Multi-GPU plumbing (one process per GPU).
 
-Only the parts of the path that shard are here (SURVEY.md §8e):
+Only the parts of the path that shard are here:
 
 * independent networks (BASELINE config 5, temperature sweeps): `shard_range` gives every rank a contiguous block of
-  networks; no data-path collective, results are gathered at the end (`gather_rates`);
-* phase 2 (BASELINE config 4): the per-a reductions are independent once the reduced A ∪ B block exists.  Every rank
-  runs `ngt_phase_two_shard(rank, world)` on every world-th a and the (1-P'_aa, tau'_a) pairs are merged with ONE
-  all-reduce(sum) (unowned entries are zero) and installed with `ngt_set_final`.  Optionally rank 0's reduced block is
-  broadcast first so that every rank reduces bit-identical input.
+  networks; no data-path collective, the per-network rates are gathered at the end (`gather_rates`);
+* phase 2 (BASELINE config 4): every rank runs its share of the phase-2 elimination tree
+  (`ngt_phase_two_shard(rank, world)`: a contiguous block of every group's members) and the (1-P'_aa, tau'_a)
+  vectors are merged with ONE all-reduce(sum) (entries of other ranks are zero).  On GPUs the all-reduce and the
+  optional broadcast of rank 0's reduced block are NCCL calls made by the C++ engine on its own stream
+  (`compute_rates_sharded` -> `ngt_phase_two_sharded`); `phase_two_sharded` is the same schedule with the reduction
+  supplied by the caller (gloo in the CPU tests);
+* one dense network over several GPUs (BASELINE config 3 at N > 1): `dense_phase_one_distributed` ->
+  `ngt_dist_phase_one`, the whole block loop in C++ with NCCL on the engine's streams.
 
+torch.distributed is used for rendezvous only (handing NCCL's unique id to the ranks, gathering a few numbers).
 The reference has nothing to compare with here: it is single-threaded ("Parallelism strategies: none").
 """
 import numpy as np
 
+from . import _capi
+
 
 def shard_range(n_items, rank, world):
-    """contiguous block [lo, hi) of `n_items` for `rank` (sizes differ by at most one)"""
+    """contiguous block [lo, hi) of `n_items` for `rank` (sizes differ by at most one, remainder to the low ranks;
+    the same split ngt_phase_two_shard uses for the members of A and of B)"""
     base, extra = divmod(int(n_items), int(world))
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
@@ -26,8 +34,22 @@ def _dist():
     return dist
 
 
+_comms = {}
+
+
+def communicator(group=None, device=None):
+    """the library's NCCL communicator for `group` (created once per process and group)"""
+    import torch
+    if device is None:
+        device = torch.cuda.current_device()
+    key = (id(group) if group is not None else None, int(device))
+    if key not in _comms:
+        _comms[key] = _capi.Comm.from_torch(device=device, group=group)
+    return _comms[key]
+
+
 def all_reduce_sum(array, group=None):
-    """sum a float64 numpy array over the ranks of `group` (moves through the GPU when the backend is NCCL)"""
+    """sum a small float64 numpy array over the ranks of `group` (host-side plumbing: gathers of a few rates)"""
     import torch
     dist = _dist()
     t = torch.from_numpy(np.ascontiguousarray(array, np.float64).copy())
@@ -37,42 +59,25 @@ def all_reduce_sum(array, group=None):
     return t.cpu().numpy()
 
 
-class _DeviceBlock(object):
-    """exposes a raw device pointer through __cuda_array_interface__ so torch can broadcast it in place"""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
-
-
-def broadcast_reduced_block(handle, src=0, group=None):
-    """NCCL broadcast of the phase-1-reduced (|A|+|B|) x ld block (incl. tau column) from rank `src` into every rank's
-    engine memory (8 MiB at |A|+|B| = 1024)."""
-    import torch
-    ptr, n = handle.reduced_block_dev()
-    t = torch.as_tensor(_DeviceBlock(ptr, n), device="cuda")
-    _dist().broadcast(t, src=src, group=group)
-    torch.cuda.synchronize()
-
-
 def phase_two_sharded(handle, rank, world, reduce_fn=all_reduce_sum):
-    """per-a reductions of this rank's share + one all-reduce; afterwards every rank's handle returns the full rates.
-    `handle` needs phase_two_shard(rank, world), final() -> (om, tau) and set_final(om, tau)."""
+    """this rank's share of phase 2 + one all-reduce supplied by the caller; afterwards every rank's handle returns the
+    full rates.  `handle` needs phase_two_shard(rank, world), final() -> (om, tau) and set_final(om, tau)."""
     handle.phase_two_shard(rank, world)
     om, tau = handle.final()
-    m = om.size
-    merged = reduce_fn(np.concatenate([om, tau]))
-    handle.set_final(merged[:m], merged[m:])
-    return merged[:m], merged[m:]
+    shape = np.shape(om)
+    merged = reduce_fn(np.concatenate([np.ravel(om), np.ravel(tau)]))
+    half = merged.size // 2
+    om, tau = merged[:half].reshape(shape), merged[half:].reshape(shape)
+    handle.set_final(om, tau)
+    return om, tau
 
 
-def compute_rates_sharded(handle, group=None, broadcast=False):
-    """phase 1 on every rank (replicated), optional broadcast of rank 0's reduced block, sharded phase 2."""
-    dist = _dist()
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+def compute_rates_sharded(handle, group=None, broadcast=False, comm=None):
+    """phase 1 on every rank (replicated), optional NCCL broadcast of rank 0's reduced block, sharded phase 2 with the
+    merge done by NCCL on the engine's stream.  Returns the device time of the phase-2 part in ms."""
+    comm = comm or communicator(group)
     handle.phase_one()
-    if broadcast and world > 1:
-        broadcast_reduced_block(handle, 0, group)
-    return phase_two_sharded(handle, rank, world, lambda a: all_reduce_sum(a, group))
+    return handle.phase_two_sharded(comm, broadcast_root=broadcast)
 
 
 def gather_rates(local_rates, n_total, rank, world, group=None):
@@ -86,47 +91,34 @@ def gather_rates(local_rates, n_total, rank, world, group=None):
 
 # ---------------------------------------------------------------------------------------------------------------
 # One dense network over several GPUs (BASELINE config 3 at N > 1): 1-D block-cyclic columns + panel broadcast.
-# The engine exposes the per-block stages (include/ngt_b200.h, ngt_dist_*); the collectives are issued here.
 # ---------------------------------------------------------------------------------------------------------------
+def dense_phase_one_distributed(handle, group=None, comm=None):
+    """Phase 1 of one complete network spread over the ranks of `group` (every rank holds a handle created from the
+    same rate matrix).  Per outer block: all-reduce of the block rows' outside mass (for the subtraction-free
+    pivots), panel factorisation on the owning rank, NCCL broadcast of the factored panel, trailing update of the
+    own columns on every rank -- all enqueued by the C++ engine on its streams without a host synchronisation
+    between blocks.  Afterwards handle.phase_two() / rates() work as usual on every rank.
+    Returns the device time in ms."""
+    comm = comm or communicator(group)
+    return handle.dist_phase_one(comm)
+
+
+class _DeviceBlock(object):
+    """exposes a raw device pointer through __cuda_array_interface__"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+
 def _dev_tensor(ptr, n):
     import torch
     return torch.as_tensor(_DeviceBlock(ptr, n), device="cuda")
 
 
-def dense_phase_one_distributed(handle, group=None):
-    """Phase 1 of one complete network spread over the ranks of `group` (every rank holds a handle created from the
-    same rate matrix).  Per outer block: all-reduce of the block rows' outside mass (for the subtraction-free
-    pivots), panel factorisation on the owning rank, NCCL broadcast of the factored panel, trailing update of the
-    own columns on every rank.  Afterwards handle.phase_two() / rates() work as usual on every rank.
-
-    The engine runs the bulk of each trailing update on its own second stream while the next block's collectives
-    and panel proceed, so only the stream the collectives were issued on is synchronised here — never the device."""
-    import torch
-    dist = _dist()
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    cur = torch.cuda.current_stream()
-    handle.dist_begin(rank, world)
-    npiv, block = handle.dist_info()
-    for J in range(0, npiv, block):
-        p, n = handle.dist_rowsum(J)
-        dist.all_reduce(_dev_tensor(p, n), op=dist.ReduceOp.SUM, group=group)
-        cur.synchronize()             # the engine works on its own streams: the collective must have landed
-        owner = (J // block) % world
-        if rank == owner:
-            handle.dist_factor(J)
-        p, n = handle.dist_panel(J)
-        dist.broadcast(_dev_tensor(p, n), src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
-        cur.synchronize()
-        handle.dist_apply(J)
-    p, n = handle.dist_root()
-    dist.all_reduce(_dev_tensor(p, n), op=dist.ReduceOp.SUM, group=group)
-    cur.synchronize()
-    handle.dist_finish()
-
-
 def dense_phase_one_emulated(handles):
-    """The same schedule with the ranks emulated by `handles` inside ONE process on ONE GPU (tests): the collectives
-    become explicit sums / copies between the handles' device buffers."""
+    """The same schedule through the staged C ABI (ngt_dist_rowsum / factor / panel / apply) with the ranks emulated by
+    `handles` inside ONE process on ONE GPU (tests): the collectives become explicit sums / copies between the
+    handles' device buffers."""
     import torch
     world = len(handles)
     for g, h in enumerate(handles):
