@@ -43,6 +43,8 @@ class Stats(ctypes.Structure):
         d = {f: getattr(self, f) for f, _t in self._fields_ if f != "reserved"}
         d["schur_launches"] = self.reserved[0]
         d["ms_profiled_pass"] = self.reserved[1]
+        d["h2d_bytes_total"] = int(self.reserved[2])   # process-wide counters of the library's host<->device copies
+        d["d2h_bytes_total"] = int(self.reserved[3])
         return d
 
 

@@ -15,6 +15,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -113,6 +114,9 @@ struct DevCache {
 };
 DevCache g_cache;
 
+// bytes moved between host and device by this library (bench.py reports them per end-to-end step)
+std::atomic<long long> g_h2d_bytes{0}, g_d2h_bytes{0};
+
 template <class T>
 struct DevBuf {
     T *p = nullptr;
@@ -136,7 +140,10 @@ struct DevBuf {
     }
     void upload(const std::vector<T> &v) {
         alloc(v.size());
-        if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        if (!v.empty()) {
+            CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+            g_h2d_bytes += (long long)(v.size() * sizeof(T));
+        }
     }
     void release() {
         if (p) g_cache.put(p, cap);
@@ -321,6 +328,7 @@ struct Engine {
     bool use_graph = std::getenv("NGT_B200_NO_GRAPH") == nullptr;
     bool use_cluster = std::getenv("NGT_B200_NO_CLUSTER") == nullptr;
     bool capturing = false, last_step_graph = false;
+    bool p1_timed = false, p2_timed = false;   // the phase events of the last pass were recorded (not a graph replay)
     long long steps_done = 0;
     cudaGraphExec_t graph_exec = nullptr;
     const double *graph_dK = nullptr;
@@ -885,6 +893,7 @@ struct Engine {
         }
         CK(cudaGetLastError());     // a bad launch configuration must not pass silently
         if (!capturing) CK(cudaEventRecord(ev[2], stream));
+        p1_timed = !capturing;
         have_phase1 = true;
         have_phase2 = false;
         have_backsub = false;
@@ -905,6 +914,7 @@ struct Engine {
         }
         tau0.resize((size_t)nbatch * n);
         CK(cudaMemcpyAsync(tau0.data(), d_tau0.p, tau0.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        g_d2h_bytes += (long long)((root.size() + tau0.size()) * sizeof(double));
     }
 
     void phase_two(int rank = 0, int nranks = 1) {
@@ -934,6 +944,7 @@ struct Engine {
         st.n_launches++;
         CK(cudaGetLastError());
         if (!capturing) CK(cudaEventRecord(ev[4], stream));
+        p2_timed = !capturing;
     }
 
     // One whole numeric step (ingest + phase 1 + phase 2 kernels).  The launch sequence depends only on the
@@ -974,6 +985,7 @@ struct Engine {
         }
         CK(cudaGraphLaunch(graph_exec, stream));
         last_step_graph = true;
+        p1_timed = p2_timed = false;
         have_phase1 = true;
         have_phase2 = false;
         have_backsub = false;
@@ -984,14 +996,15 @@ struct Engine {
         final_tau.resize((size_t)nbatch * m);
         CK(cudaMemcpyAsync(final_om.data(), d_om.p, final_om.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
         CK(cudaMemcpyAsync(final_tau.data(), d_ftau.p, final_tau.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        g_d2h_bytes += (long long)(2 * final_om.size() * sizeof(double));
         download_root();
         check_errflag("phase two");
-        if (!last_step_graph) {
-            float ms = 0;
+        float ms = 0;
+        if (p1_timed) {
             cudaEventElapsedTime(&ms, ev[0], ev[1]); st.ms_ingest = ms;
             cudaEventElapsedTime(&ms, ev[1], ev[2]); st.ms_phase1 = ms;
-            cudaEventElapsedTime(&ms, ev[3], ev[4]); st.ms_phase2 = ms;
         }
+        if (p2_timed) { cudaEventElapsedTime(&ms, ev[3], ev[4]); st.ms_phase2 = ms; }
         have_phase2 = true;
         if (nranks == 1) finish_rates();
     }
@@ -1212,6 +1225,7 @@ struct Engine {
         have_phase1 = true;
         have_phase2 = have_backsub = false;
         last_step_graph = true;   // no per-phase events were recorded for this pass
+        p1_timed = false;
     }
 
     // staged, synchronous variants (C ABI ngt_dist_*)
@@ -1245,9 +1259,10 @@ struct Engine {
     void dist_phase_one(Comm &cm, double *ms) {
         NcclApi &nc = NcclApi::get();
         if (cm.device != device) throw InvalidError("communicator and handle live on different devices");
+        CK(cudaSetDevice(device));
+        CK(cudaEventRecord(ev[0], stream));     // the timed region includes the ingest kernel, like a single-GPU step
         dist_begin(cm.rank, cm.world);
         const int block = ngt::NB_OUTER;
-        CK(cudaEventRecord(ev[0], stream));
         for (int J = 0; J < (int)S.nI; J += block) {
             dist_rowsum_enqueue(J);
             NK(nc.AllReduce(d_spart.p, d_spart.p, (size_t)block, NcclApi::F64, NcclApi::SUM, cm.comm, stream));
@@ -1325,6 +1340,8 @@ struct Engine {
         xq.resize((size_t)nbatch * npos * 2);
         CK(cudaMemcpyAsync(xq.data(), d_x.p, xq.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
+        g_h2d_bytes += (long long)(nbatch * x0.size() * sizeof(double));
+        g_d2h_bytes += (long long)(xq.size() * sizeof(double));
         have_backsub = true;
     }
 };
@@ -1454,6 +1471,7 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
         E->d_k.alloc((size_t)nnz * E->nbatch);
         if (k) {
             CK(cudaMemcpy(E->d_k.p, k, (size_t)nnz * E->nbatch * sizeof(double), cudaMemcpyHostToDevice));
+            g_h2d_bytes += (long long)((size_t)nnz * E->nbatch * sizeof(double));
             E->values_loaded = true;
         }
     });
@@ -1612,6 +1630,7 @@ void build_dense(Engine *E, int64_t n, const double *K, bool on_device, int64_t 
         } else {
             E->d_K_owned.alloc((size_t)n * n * E->nbatch);
             CK(cudaMemcpy(E->d_K_owned.p, K, (size_t)n * n * E->nbatch * sizeof(double), cudaMemcpyHostToDevice));
+            g_h2d_bytes += (long long)((size_t)n * n * E->nbatch * sizeof(double));
             E->d_K = E->d_K_owned.p;
         }
         E->values_loaded = true;
@@ -1741,12 +1760,14 @@ static int set_rates_any(ngt_handle h, const double *k, bool dev) {
                 if (!E->d_K_owned.p) E->d_K_owned.alloc(cnt);
                 CK(cudaMemcpyAsync(E->d_K_owned.p, k, cnt * sizeof(double), cudaMemcpyHostToDevice, E->stream));
                 CK(cudaStreamSynchronize(E->stream));
+                g_h2d_bytes += (long long)(cnt * sizeof(double));
                 E->d_K = E->d_K_owned.p;
             }
         } else {
             CK(cudaMemcpyAsync(E->d_k.p, k, cnt * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                E->stream));
             CK(cudaStreamSynchronize(E->stream));
+            if (!dev) g_h2d_bytes += (long long)(cnt * sizeof(double));
         }
         E->values_loaded = true;
         E->have_phase1 = E->have_phase2 = E->have_backsub = false;
@@ -1916,6 +1937,8 @@ int ngt_get_stats(ngt_handle h, ngt_stats *st) {
     return guard([&] {
         Engine *E = eng(h);
         *st = E->st;
+        st->reserved[2] = (double)g_h2d_bytes.load();   // process-wide byte counters (differences are what matter)
+        st->reserved[3] = (double)g_d2h_bytes.load();
     });
 }
 
@@ -1943,14 +1966,20 @@ int ngt_profile_schur(ngt_handle h, double *ms_schur, double *flops, int64_t *la
     return guard([&] {
         Engine *E = eng(h);
         CK(cudaSetDevice(E->device));
+        // one stream for this pass: with the trailing updates on the look-ahead stream, event pairs on two streams
+        // overlap in time and their sum could exceed the duration of the pass
+        const bool la = E->use_lookahead;
         E->profile_schur = true;
+        E->use_lookahead = false;
         try {
             E->phase_one();
         } catch (...) {
             E->profile_schur = false;
+            E->use_lookahead = la;
             throw;
         }
         E->profile_schur = false;
+        E->use_lookahead = la;
         CK(cudaStreamSynchronize(E->stream));
         E->check_errflag("phase one");
         double tot = 0;

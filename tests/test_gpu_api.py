@@ -164,3 +164,56 @@ def test_two_state_rates_three_state():
         assert abs(red.get_rate_AB() - 1.0) < 1e-7
         red.compute_committors()
         assert abs(red.get_rate_AB_SS() - 1.5) < 1e-7
+
+
+def test_graph_reduction_node_that_cannot_reach_the_other_group():
+    """0 can only shuttle between itself and 2: after phase 2 nothing but its self loop is left, and the reference
+    raises a bare Exception (reference _kmc_rates.py:227-228)"""
+    from kmc_rates_b200 import GraphReduction
+    rates = {(1, 0): 1.0, (0, 2): 1.0, (2, 0): 1.0, (1, 2): 1.0}
+    reducer = GraphReduction(rates, [0], [1])
+    with pytest.raises(Exception, match="node 0 is not connected"):
+        reducer.compute_rates()
+
+
+def test_graph_reduction_weights_covering_only_A():
+    """the reference reads weights lazily per group (reference _kmc_rates.py:168-172): a plain dict over A is enough for
+    get_rate_AB, and get_rate_BA then fails with KeyError"""
+    from kmc_rates_b200 import GraphReduction, synth
+    from oracle.py_ngt import PyGraphReduction
+    A, B = [0, 1, 2], [7, 8]
+    rates = synth.random_connected_graph(12, 24, A + B, seed=5)
+    w = {0: 0.2, 1: 0.5, 2: 0.3}
+    reducer = GraphReduction(rates, A, B, weights=w)
+    reducer.compute_rates()
+    ref = PyGraphReduction(rates, A, B, weights=w)
+    ref.compute_rates()
+    assert abs(reducer.get_rate_AB() - ref.get_rate_AB()) < 1e-9 * ref.get_rate_AB()
+    with pytest.raises(KeyError):
+        reducer.get_rate_BA()
+
+
+def test_two_state_rates_with_absorbing_product_nodes():
+    """B without outgoing rates: the reference's linear-algebra classes treat B as absorbing and never read rates out
+    of it (reference rates_linalg.py:246-285)"""
+    from kmc_rates_b200 import synth
+    from kmc_rates_b200.rates_linalg import TwoStateRates
+    from oracle.py_linalg import TwoStateRatesCOO
+    A, B = [0, 1], [8, 9]
+    rates = synth.random_connected_graph(10, 24, A + B, seed=11)
+    rates = {uv: r for uv, r in rates.items() if uv[0] not in B}      # products become pure sinks
+    assert any(v in B for (_u, v) in rates)
+    twin = TwoStateRates(rates, A, B)
+    twin.compute_rates()
+    twin.compute_committors()
+    labels = sorted({u for uv in rates for u in uv})
+    idx = {u: i for i, u in enumerate(labels)}
+    src = np.array([idx[u] for (u, _v) in rates]); dst = np.array([idx[v] for (_u, v) in rates])
+    k = np.array(list(rates.values()))
+    la = TwoStateRatesCOO(len(labels), src, dst, k, [idx[a] for a in A], [idx[b] for b in B])
+    la.compute_rates()
+    la.compute_committors()
+    assert abs(twin.get_rate_AB() - la.get_rate_AB()) < 1e-9 * la.get_rate_AB()
+    for u in labels:
+        if u not in A and u not in B:
+            assert abs(twin.get_committor(u) - la.q[idx[u]]) < 1e-9

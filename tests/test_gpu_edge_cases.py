@@ -131,3 +131,77 @@ def test_large_ill_conditioned_landscape_against_linear_solve_and_properties():
     la = TwoStateRatesCOO(n, src, dst, k, A, B)
     la.compute_committors()
     assert np.nanmax(np.abs(q - la.q)) < 1e-6
+
+
+def test_set_rates_with_a_device_tensor_produced_on_the_callers_stream():
+    """rate constants produced by torch kernels (on torch's stream) and handed over as a CUDA tensor: the engine's
+    own non-blocking streams must see the finished values (sparse: copied in; dense: borrowed)"""
+    import torch
+    from kmc_rates_b200 import synth
+    from kmc_rates_b200._capi import Handle
+    n, src, dst, k, A, B = synth.landscape_2d(40, T=0.3, seed=4)
+    h = Handle.from_coo(n, src, dst, k, A, B)
+    h.compute_rates()
+    base = h.rates().copy()
+    kd = torch.from_numpy(k).cuda()
+    for scale in (2.0, 0.25):
+        big = torch.randn(4096, 4096, device="cuda") @ torch.randn(4096, 4096, device="cuda")   # keep torch's stream busy
+        kd2 = kd * scale + 0.0 * big[0, 0].double()
+        h.set_rates(kd2)
+        h.compute_rates()
+        assert np.allclose(h.rates(), base * scale, rtol=1e-12, atol=0)     # all rates are linear in the rate constants
+    s2, d2, k2 = synth.complete_random(300, seed=2)
+    K = torch.zeros(300, 300, dtype=torch.float64, device="cuda")
+    K[torch.from_numpy(s2).cuda(), torch.from_numpy(d2).cuda()] = torch.from_numpy(k2).cuda()
+    hd = Handle.from_dense(K, [0], [299])
+    hd.compute_rates()
+    r0 = hd.rates().copy()
+    K3 = K.clone().mul_(3.0)
+    hd.set_rates(K3)
+    hd.compute_rates()
+    assert np.allclose(hd.rates(), 3.0 * r0, rtol=1e-12, atol=0)
+
+
+def test_batched_handle_final_and_single_network_getters():
+    """final() of a batched handle has one row per network; getters that return one network refuse a batch"""
+    from kmc_rates_b200 import synth
+    from kmc_rates_b200._capi import Handle
+    from oracle.cpu_ngt import CpuNGT
+    n, src, dst, k, A, B = synth.landscape_groups(12, 3, 2, T=0.3, seed=9)
+    ks = np.stack([k, 2.0 * k, k ** 1.1])
+    h = Handle.from_coo(n, src, dst, ks.ravel(), A, B, nbatch=3)
+    h.compute_rates()
+    om, tau = h.final()
+    assert om.shape == (3, 5) and tau.shape == (3, 5)
+    for b in range(3):
+        cpu = CpuNGT(n, src, dst, ks[b], A, B, kind="port")
+        cpu.compute_rates()
+        o, t = cpu.final()
+        assert np.allclose(om[b], o, rtol=1e-9, atol=0) and np.allclose(tau[b], t, rtol=1e-9, atol=0)
+        assert np.allclose(h.rates()[b], cpu.rates(), rtol=1e-9, atol=0)
+    h.set_final(om, tau)                       # symmetric with final(): nbatch x (|A|+|B|)
+    with pytest.raises(ValueError):
+        h.set_final(om[0], tau[0])
+    for getter in (h.reduced, h.committors, h.mfpt, h.initial_tau):
+        with pytest.raises(ValueError):
+            getter()
+
+
+def test_phase_two_tree_odd_group_sizes_and_weights_against_the_reference():
+    """phase 2 (a binary tree of eliminations here, a loop over a in the reference, ngt.hpp:362-431) on group sizes
+    that are not powers of two, including one-member groups, against the compiled reference when present"""
+    from kmc_rates_b200 import NGT, synth
+    from oracle.cpu_ngt import CpuNGT, best_kind
+    for nA, nB, seed in [(1, 7, 1), (5, 1, 2), (13, 11, 3), (33, 2, 4), (64, 65, 5)]:
+        n, src, dst, k, A, B = synth.landscape_groups(18, nA, nB, T=0.3, seed=seed)
+        rng = np.random.default_rng(seed)
+        w = {int(x): float(rng.uniform(0.1, 1.0)) for x in A + B}
+        g = NGT.from_coo(n, src, dst, k, A, B, weights=w)
+        g.compute_rates()
+        cpu = CpuNGT(n, src, dst, k, A, B, weights=w, kind=best_kind())
+        cpu.compute_rates()
+        got = np.array([g.get_rate_AB(), g.get_rate_BA(), g.get_rate_AB_SS(), g.get_rate_BA_SS()])
+        assert np.allclose(got, cpu.rates(), rtol=1e-9, atol=0), (nA, nB)
+        om, tau = g._h.final()
+        o, t = cpu.final()
+        assert np.allclose(om, o, rtol=1e-9, atol=0) and np.allclose(tau, t, rtol=1e-9, atol=0), (nA, nB)

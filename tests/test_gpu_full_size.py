@@ -97,3 +97,32 @@ def test_config5_batched_sweep_4096_networks():
         cpu.compute_rates()
         r = cpu.rates()
         assert abs(kab[b] - r[0]) < 1e-9 * r[0] and abs(kba[b] - r[1]) < 1e-9 * r[1]
+
+
+def test_config2_ill_conditioned_T003_full_size():
+    """SURVEY §8(d)'s ill-conditioned variant of config 2 at full size: T = 0.03, rate constants down to ~1e-29, P_xx -> 1
+    after a few eliminations.  No CPU elimination reaches this size and the LU-based linear solve loses digits here, so
+    the evidence is: (1) conservation and range properties, (2) two different elimination orders and two different GEMM
+    paths (tensor-core and scalar) agree to 1e-9 -- subtraction-free pivots make every order accurate, a cancelling
+    1 - P_xx would not survive this -- and (3) the sparse LU solve where it still holds (1e-6)."""
+    from kmc_rates_b200 import NGT, synth
+    from oracle.py_linalg import TwoStateRatesCOO
+    n, src, dst, k, A, B = synth.landscape_2d(316, T=0.03, seed=0)
+    assert k.min() < 1e-25
+    g = NGT.from_coo(n, src, dst, k, A, B)
+    g.compute_rates_and_committors()
+    P, _tau = g._h.reduced()
+    assert np.max(np.abs(P.sum(axis=1) - 1.0)) < 1e-12
+    q, t = g.get_committor_array(), g.get_mfpt_array()
+    assert np.nanmin(q) >= 0.0 and np.nanmax(q) <= 1.0 + 1e-12
+    assert np.all(t[np.isfinite(t)] >= 0.0)
+    r = np.array([g.get_rate_AB(), g.get_rate_BA(), g.get_rate_AB_SS(), g.get_rate_BA_SS()])
+    assert np.all(np.isfinite(r)) and np.all(r > 0)
+    g2 = NGT.from_coo(n, src, dst, k, A, B, leaf_size=24, gemm_path=1)      # another elimination tree, scalar DFMA updates
+    g2.compute_rates_and_committors()
+    r2 = np.array([g2.get_rate_AB(), g2.get_rate_BA(), g2.get_rate_AB_SS(), g2.get_rate_BA_SS()])
+    assert np.max(np.abs(r2 - r) / r) < 1e-9
+    assert np.nanmax(np.abs(g2.get_committor_array() - q)) < 1e-9
+    la = TwoStateRatesCOO(n, src, dst, k, A, B)
+    la.compute_committors()
+    assert np.nanmax(np.abs(q - la.q)) < 1e-6

@@ -49,13 +49,13 @@ def _random_network(rng):
 @pytest.mark.parametrize("seed", range(40))
 def test_random_network_matches_oracle(seed):
     from kmc_rates_b200 import NGT
-    from oracle.cpu_ngt import CpuNGT
+    from oracle.cpu_ngt import CpuNGT, best_kind
     rng = np.random.default_rng(1000 + seed)
     n, src, dst, k, A, B, w = _random_network(rng)
     leaf = int(rng.choice([0, 4, 8, 16]))
     g = NGT.from_coo(n, src, dst, k, A, B, weights=w, leaf_size=leaf, gemm_path=int(rng.choice([0, 1, 2])))
     g.compute_rates_and_committors()
-    cpu = CpuNGT(n, src, dst, k, A, B, weights=w, kind="port")
+    cpu = CpuNGT(n, src, dst, k, A, B, weights=w, kind=best_kind())   # the compiled reference itself when it is present
     cpu.compute_rates_and_committors()
     got = [g.get_rate_AB(), g.get_rate_BA(), g.get_rate_AB_SS(), g.get_rate_BA_SS()]
     assert rel_err(got, cpu.rates()) < 1e-9
