@@ -256,7 +256,7 @@ def cpu_config_points(kind, cores, c5_sample):
     return out, {"c1": c1[3], "c5": {r[1]: r[3] for r in c5}}
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -289,7 +289,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -567,8 +567,18 @@ def main():
     ap.add_argument("--no-sharded", action="store_true")
     ap.add_argument("--dense-n", type=int, default=16384)
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON record: everything else any library prints there (NCCL announces its
+    # version on stdout when a communicator is created) is sent to stderr; the record goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     from kmc_rates_b200 import synth, _capi
@@ -788,7 +798,7 @@ def main():
     if dist is not None:
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
 
 
 if __name__ == "__main__":

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libngt_b200.so")
+# NGT_B200_LIB selects another build of the same library (A/B timing of kernel variants; scripts/build_variant.sh)
+LIB_PATH = os.environ.get("NGT_B200_LIB") or os.path.join(_HERE, "csrc", "libngt_b200.so")
 
 NGT_OK, NGT_E_INVALID, NGT_E_CUDA, NGT_E_STATE, NGT_E_NUMERIC = 0, 1, 2, 3, 4
 

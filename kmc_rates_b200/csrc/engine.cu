@@ -259,14 +259,20 @@ struct Engine {
     DevBuf<int> d_err;
     DevBuf<double> d_tau0;
     // sparse ingest
-    DevBuf<long long> d_row_ptr, d_dest, d_tau_dest;
+    DevBuf<long long> d_row_ptr, d_dest, d_tau_dest, d_dstnodes;
     DevBuf<int> d_row_node, d_korig;
     DevBuf<double> d_k;
     int n_rows = 0;
     // dense ingest
     DevBuf<double> d_K_owned;
     const double *d_K = nullptr;
-    DevBuf<int> d_pos;
+    DevBuf<int> d_pos, d_node_at;
+    // batches of small complete networks: one CTA per network does ingest + phase 1 (kernels.cu, dense_network_kernel);
+    // the cross-check GEMM paths and large or single networks keep the multi-kernel path
+    bool use_dense_net() const {
+        static const bool off = std::getenv("NGT_B200_NO_DENSE_NET") != nullptr;
+        return !off && dense && S.nI > 0 && opt.gemm_path == 0 && n <= ngt::DENSE_NET_MAX_N && (nbatch >= 8 || n <= 160);
+    }
     // phase 2
     DevBuf<double> d_p2pool;
     long long p2_stride = 0;
@@ -839,6 +845,7 @@ struct Engine {
         CK(cudaStreamSynchronize(stream));
         if (flag) {
             CK(cudaMemset(d_err.p, 0, sizeof(int)));
+            if (flag & 4) throw std::logic_error(std::string(where) + ": a rate has no slot in its front");
             if (flag & 2) throw NumericError(std::string(where) + ": a node has no outgoing rate (tau = 1/0)");
             throw NumericError(std::string(where) +
                                ": a pivot 1-P_xx was zero or not finite (node cannot reach the rest of the graph)");
@@ -876,6 +883,20 @@ struct Engine {
         st.reserved[0] = 0;
         prof_used = 0;
         if (!capturing) CK(cudaEventRecord(ev[0], stream));
+        if (use_dense_net()) {
+            // ingest + elimination of every intermediate + the reduced graph in ONE launch, one CTA per network
+            if (!capturing) CK(cudaEventRecord(ev[1], stream));
+            ngt::launch_dense_network(d_K, (int)n, nbatch, d_node_at.p, (int)S.nI, d_pool.p, pool_stride, h_fronts[0],
+                                      h_fronts[S.root_id], d_tau0.p, d_err.p, stream);
+            st.n_launches++;
+            CK(cudaGetLastError());
+            if (!capturing) CK(cudaEventRecord(ev[2], stream));
+            p1_timed = !capturing;
+            have_phase1 = true;
+            have_phase2 = false;
+            have_backsub = false;
+            return;
+        }
         ingest();
         if (!capturing) CK(cudaEventRecord(ev[1], stream));
         ngt::LaunchCtx c = ctx(d_pool.p, pool_stride, d_fronts.p);
@@ -1448,8 +1469,11 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
     std::vector<int64_t> &outdeg = ix.outptr;     // row pointers of the CSR-by-source entry lists
     for (int64_t a : E->A) if (!present[a]) throw InvalidError("an element in the reactant set (A) is not in the graph");
     for (int64_t b : E->B) if (!present[b]) throw InvalidError("an element in the product set (B) is not in the graph");
-    for (int64_t u = 0; u < n; ++u)
+    bool all_present = true;
+    for (int64_t u = 0; u < n; ++u) {
         if (present[u] && outdeg[u + 1] == outdeg[u]) throw InvalidError("node " + std::to_string(u) + " has no outgoing rate");
+        all_present = all_present && present[u];
+    }
     tm.lap("index edges (validate, CSR buckets, adjacency)");
     // Beside the analysis (which leaves cores idle while it walks the top of the dissection tree): (1) the device is
     // initialised and the rate constants are uploaded, (2) the entries that survive de-duplication are counted per
@@ -1473,6 +1497,20 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
             CK(cudaMemcpy(E->d_k.p, k, (size_t)nnz * E->nbatch * sizeof(double), cudaMemcpyHostToDevice));
             g_h2d_bytes += (long long)((size_t)nnz * E->nbatch * sizeof(double));
             E->values_loaded = true;
+        }
+        // Every node named by a rate (the usual case): the CSR-by-source edge index doubles as the ingest kernel's row
+        // structure and the rate -> slot table is built on the device once the analysis is known, so the index and
+        // the destination ids go up now, beside the ordering.  (Networks with absent ids, duplicate rates or pruned
+        // components take the host-built table below, which overwrites these.)
+        if (all_present) {
+            static_assert(sizeof(long long) == sizeof(int64_t), "row pointers are uploaded as they are");
+            E->d_row_ptr.alloc((size_t)n + 1);
+            CK(cudaMemcpy(E->d_row_ptr.p, outdeg.data(), ((size_t)n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+            E->d_korig.alloc((size_t)nnz);
+            CK(cudaMemcpy(E->d_korig.p, ix.ent.data(), (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
+            E->d_dstnodes.alloc((size_t)nnz);
+            CK(cudaMemcpy(E->d_dstnodes.p, dst, (size_t)nnz * sizeof(int64_t), cudaMemcpyHostToDevice));
+            g_h2d_bytes += (long long)(((size_t)n + 1) * 8 + (size_t)nnz * 12);
         }
     });
     std::vector<int32_t> &row_cnt = W.row_cnt;
@@ -1540,9 +1578,39 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
         CK(cudaSetDevice(E->device));
         E->upload_structure();
     });
+    count_task.finish();
+    {
+        int64_t kept_entries = 0;
+        for (int64_t u = 0; u < n; ++u) kept_entries += row_cnt[u];
+        bool was_pruned = false;
+        for (int64_t u = 0; u < n && !was_pruned; ++u) was_pruned = !present[u];
+        if (all_present && !was_pruned && kept_entries == nnz) {
+            // ---- rate -> slot table on the device (no duplicates, nothing absent or pruned: row u = node u) ----------
+            structure_task.finish();
+            CK(cudaSetDevice(E->device));
+            std::vector<int> ffirst(S.fronts.size());
+            for (size_t i = 0; i < S.fronts.size(); ++i) ffirst[i] = S.fronts[i].first;
+            DevBuf<int> d_posn, d_pos_front, d_ffirst;
+            d_posn.upload(S.pos);
+            d_pos_front.upload(S.pos_front);
+            d_ffirst.upload(ffirst);
+            E->d_dest.alloc((size_t)nnz);
+            E->d_tau_dest.alloc((size_t)n);
+            E->d_row_node.release();                     // null: the ingest kernel reads row u as node u
+            E->n_rows = (int)n;
+            ngt::launch_slot_table((int)n, E->d_row_ptr.p, E->d_korig.p, E->d_dstnodes.p, d_posn.p, d_pos_front.p,
+                                   E->d_fronts.p, d_ffirst.p, E->d_fidx.p, E->d_idx_off.p, E->d_dest.p, E->d_tau_dest.p,
+                                   E->d_err.p, E->stream);
+            CK(cudaGetLastError());
+            E->check_errflag("slot table");              // synchronises the stream: the temporaries may go
+            E->d_dstnodes.release();
+            tm.lap("slot table on the device");
+            E->st.ms_symbolic = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            return;
+        }
+    }
     // CSR by source over present nodes, (src,dst) duplicates resolved "last wins"; rows = present nodes in id order,
     // each worker thread writes the source indices and slots of a contiguous slice of rows
-    count_task.finish();
     std::vector<int> &row_node = W.row_node;
     row_node.clear();
     for (int64_t u = 0; u < n; ++u)
@@ -1619,6 +1687,7 @@ void build_dense(Engine *E, int64_t n, const double *K, bool on_device, int64_t 
     ngt::analyse_dense(n, E->A, E->B, E->S);
     E->init_device();
     E->d_pos.upload(E->S.pos);
+    E->d_node_at.upload(E->S.node_at);
     E->upload_structure();
     E->make_tensor_maps();
     if (K) {

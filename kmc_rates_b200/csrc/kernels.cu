@@ -216,6 +216,170 @@ __device__ __forceinline__ double gj_tail_sum(const double (&X)[GJ_COLS], int t)
 }
 __device__ __forceinline__ void gj_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(GJ_WARPS * 32) : "memory"); }
 
+// -----------------------------------------------------------------------------------------------------
+// Blocked subtraction-free Gauss-Jordan: W = (I - T)^-1 of a 32-pivot panel in 8-pivot blocks (4 warps).
+//   working matrix G: NB_INNER x GJ_LD in shared memory; columns 0..31 hold T (diagonal ignored), column 32 the mass s
+//   that leaves the panel.  Block step b (pivots B = 8b..8b+7):
+//     (1) warp 0 inverts the 8 x 8 diagonal block with the scalar GTH recurrence -- pivot d_p = sum_{q>p, q in B} T_pq +
+//         sigma_p, sigma_p = the row's mass into later blocks and out of the panel -> W_b = (I - T_BB)^-1;
+//     (2) all warps, on the FP64 tensor cores (DMMA m8n8k4): the block row becomes Y = W_b G[B][other columns], every
+//         other row tile gets G[r][c] += G[r][B] Y[B][c]  (8 x 8 x 8 products, one 8-column tile of G per warp; the s
+//         column rides as a fifth tile), and the block's own columns become G[r][B] W_b: they join the inverse.
+//   After the four block steps columns 0..31 of G hold W.  Every quantity is a sum of products of non-negative
+//   numbers, as in the scalar recurrence (Wales' 1-P_xx as a sum of off-diagonal probabilities, blocked).
+//   The scalar 32-step recurrence (kept below under NGT_OLD_GJ) issued ~37 warp-wide FP64 instructions per pivot at
+//   8 cycles each on all four schedulers (690 cycles per pivot measured); here the scalar chain runs over 8 columns in
+//   one warp and the O(32^2) work per pivot moves to ~40 DMMAs per block.
+// -----------------------------------------------------------------------------------------------------
+constexpr int GJ_LD = NB_INNER + 4;      // = 4 mod 16 doubles: conflict-free DMMA fragment loads; column NB_INNER = s
+constexpr int WB_LD = 12;                // row stride of the 8 x 8 inverse W_b
+static_assert(NB_INNER == 32, "the blocked Gauss-Jordan is written for 32-pivot panels (4 warps x one 8-column tile)");
+
+// sum of the row's entries in block-local columns >= t; every lane of the row (lane = r + 8 cg) receives it
+__device__ __forceinline__ double gj8_tail(double x0, double x1, int cg, int t) {
+    double v = ((2 * cg >= t) ? x0 : 0.0) + ((2 * cg + 1 >= t) ? x1 : 0.0);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+}
+
+// (1): one warp.  lane = r + 8 cg holds row r of the 8 x 8 block, columns 2cg and 2cg+1, and a copy of sigma_r.
+// As in the 32-step version the rows stay unnormalised while they are eliminated (row u carries the factor d_u once it
+// has been the pivot) and are scaled by 1/d_u at the end; the NEXT pivot is formed one step ahead from sums of the
+// state before the current step: d_{p+1} = A + f B, A = sum_{q>p+1} T[p+1][q] + sigma_{p+1}, B = sum_{q>p+1} T[p][q] +
+// sigma_p, f = T[p+1][p] / d_p, so the chain reciprocal -> multiply -> fma -> reciprocal is all that is serial.
+__device__ __forceinline__ void gj8_invert(const double *G, int b, double *Wb, int lane, int *errflag) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int r = lane & 7, cg = lane >> 3;
+    const double *g = G + (8 * b + r) * GJ_LD;
+    double x0 = (2 * cg == r) ? 0.0 : g[8 * b + 2 * cg];
+    double x1 = (2 * cg + 1 == r) ? 0.0 : g[8 * b + 2 * cg + 1];
+    double sg = 0.0;
+    for (int c = 8 * (b + 1) + cg; c < NB_INNER; c += 4) sg += g[c];
+    sg += __shfl_xor_sync(FULL, sg, 8);
+    sg += __shfl_xor_sync(FULL, sg, 16);
+    sg += g[NB_INNER];
+    double RD = 0.0;
+    double tl = gj8_tail(x0, x1, cg, 2) + sg;
+    double dcur = __shfl_sync(FULL, gj8_tail(x0, x1, cg, 1) + sg, 0);
+    double rd = 1.0 / dcur;
+    bool bad = false;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        bad = bad || !(dcur > 0.0) || isinf(dcur);
+        const double xp0 = __shfl_sync(FULL, x0, p + 8 * cg), xp1 = __shfl_sync(FULL, x1, p + 8 * cg);
+        const double sp = __shfl_sync(FULL, sg, p);
+        const double colv = __shfl_sync(FULL, (p & 1) ? x1 : x0, r + 8 * (p >> 1));
+        double dn = 1.0, rdn = 1.0;
+        if (p < 7) {
+            const double A = __shfl_sync(FULL, tl, p + 1), B = __shfl_sync(FULL, tl, p);
+            const double cn = __shfl_sync(FULL, colv, p + 1);
+            const double fn = (cn == 0.0) ? 0.0 : cn * rd;
+            dn = fma(fn, B, A);
+            rdn = 1.0 / dn;
+        }
+        if (r == p) RD = rd;
+        // rows that do not reach p stay clean even if d_p == 0
+        const double f = (r == p || colv == 0.0) ? 0.0 : colv * rd;
+        x0 = fma(f, xp0, x0);
+        x1 = fma(f, xp1, x1);
+        sg = fma(f, sp, sg);
+        if (cg == (p >> 1)) {                      // column p joins the inverse
+            const double v = (r == p) ? 1.0 : f;
+            if (p & 1) x1 = v; else x0 = v;
+        }
+        if (p < 7) tl = gj8_tail(x0, x1, cg, p + 3) + sg;
+        rd = rdn;
+        dcur = dn;
+    }
+    if (bad && lane == 0) atomicOr(errflag, 1);
+    Wb[r * WB_LD + 2 * cg] = x0 * RD;
+    Wb[r * WB_LD + 2 * cg + 1] = x1 * RD;
+}
+
+__device__ __forceinline__ void gj_bar2_arrive() { asm volatile("bar.arrive 2, %0;" ::"n"(GJ_WARPS * 32) : "memory"); }
+__device__ __forceinline__ void gj_bar2_sync() { asm volatile("bar.sync 2, %0;" ::"n"(GJ_WARPS * 32) : "memory"); }
+
+// all GJ_WARPS warps call this convergently; G is overwritten by W (rows >= nbp zeroed), Wb is scratch (8 x WB_LD)
+__device__ __forceinline__ void gj_blocked(double *G, double *Wb, int nbp, int *errflag, int warp, int lane) {
+    const int g = lane >> 2, t4 = lane & 3;
+#pragma unroll 1
+    for (int b = 0; b < NB_INNER / 8; ++b) {
+        if (warp == 0) gj8_invert(G, b, Wb, lane, errflag);
+        gj_barrier();                                  // W_b is visible
+        // this warp's column tile: one of the three other 8-column tiles of the working matrix; warp 3: the s column
+        const int ct = warp < 3 ? (warp < b ? warp : warp + 1) : 4;
+        // operand fragments, read before anything is overwritten
+        double wa[2], bb[2], ab[3][2];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            wa[ks] = Wb[g * WB_LD + t4 + 4 * ks];
+            const double *row = G + (8 * b + t4 + 4 * ks) * GJ_LD;
+            bb[ks] = ct < 4 ? row[8 * ct + g] : (g == 0 ? row[NB_INNER] : 0.0);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int rt = i < b ? i : i + 1;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) ab[i][ks] = G[(8 * rt + g) * GJ_LD + 8 * b + t4 + 4 * ks];
+        }
+        if (warp != 3) gj_bar2_arrive();               // "my copy of the old column block is in registers"
+        // the block row: Y = W_b G[B][ct]
+        double y0 = 0.0, y1 = 0.0;
+        dmma884(y0, y1, wa[0], bb[0]);
+        dmma884(y0, y1, wa[1], bb[1]);
+        {
+            double *row = G + (8 * b + g) * GJ_LD;
+            if (ct < 4) { row[8 * ct + 2 * t4] = y0; row[8 * ct + 2 * t4 + 1] = y1; }
+            else if (t4 == 0) row[NB_INNER] = y0;
+        }
+        __syncwarp();
+        double yb[2];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const double *row = G + (8 * b + t4 + 4 * ks) * GJ_LD;
+            yb[ks] = ct < 4 ? row[8 * ct + g] : (g == 0 ? row[NB_INNER] : 0.0);
+        }
+        // every other row tile: G[rt][ct] += G[rt][B] Y
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int rt = i < b ? i : i + 1;
+            double *row = G + (8 * rt + g) * GJ_LD;
+            double c0, c1;
+            if (ct < 4) { c0 = row[8 * ct + 2 * t4]; c1 = row[8 * ct + 2 * t4 + 1]; }
+            else { c0 = (t4 == 0) ? row[NB_INNER] : 0.0; c1 = 0.0; }
+            dmma884(c0, c1, ab[i][0], yb[0]);
+            dmma884(c0, c1, ab[i][1], yb[1]);
+            if (ct < 4) { row[8 * ct + 2 * t4] = c0; row[8 * ct + 2 * t4 + 1] = c1; }
+            else if (t4 == 0) row[NB_INNER] = c0;
+        }
+        if (warp == 3) {
+            gj_bar2_sync();                            // the other warps hold their copies of the old column block
+            // column block b joins the inverse: G[rt][B] = G_old[rt][B] W_b, G[B][B] = W_b
+            double wf[2];
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) wf[ks] = Wb[(t4 + 4 * ks) * WB_LD + g];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int rt = i < b ? i : i + 1;
+                double c0 = 0.0, c1 = 0.0;
+                dmma884(c0, c1, ab[i][0], wf[0]);
+                dmma884(c0, c1, ab[i][1], wf[1]);
+                double *row = G + (8 * rt + g) * GJ_LD + 8 * b;
+                row[2 * t4] = c0;
+                row[2 * t4 + 1] = c1;
+            }
+            double *row = G + (8 * b + g) * GJ_LD + 8 * b;
+            row[2 * t4] = Wb[g * WB_LD + 2 * t4];
+            row[2 * t4 + 1] = Wb[g * WB_LD + 2 * t4 + 1];
+        }
+        gj_barrier();                                  // step b complete (also protects W_b against the next inversion)
+    }
+    // padding rows (panels with fewer than 32 pivots) were treated as isolated absorbing nodes: clear them
+    for (int i = warp * 32 + lane; i < (NB_INNER - nbp) * NB_INNER; i += GJ_WARPS * 32)
+        G[(nbp + i / NB_INNER) * GJ_LD + (i % NB_INNER)] = 0.0;
+}
+
 #ifdef NGT_PANEL_CLOCKS
 __device__ long long g_panel_clk[8];
 __device__ long long g_gj_clk[8];
@@ -247,12 +411,16 @@ panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const in
     const int je = j + nbp;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    __shared__ double Xs[NB_INNER][NB_INNER + 1];   // T on the way in, W on the way out (padded: lane = row access)
+    __shared__ double Xs[NB_INNER][GJ_LD];          // T (and s in column NB_INNER) on the way in, W on the way out
+#ifdef NGT_OLD_GJ
     __shared__ double Ss[NB_INNER];
     // Gauss-Jordan hand-over, double buffered by step parity: pivot row, pivot column, s of every row and the
     // per-warp partial sums of every row over the columns two past the pivot
     __shared__ __align__(16) double Row[2][NB_INNER], Col[2][NB_INNER], Sv[2][NB_INNER], Ps[2][GJ_WARPS][NB_INNER];
     __shared__ double D0;
+#else
+    __shared__ double Wb8[8 * WB_LD];
+#endif
     __shared__ double xs[NB_INNER * (CW + 4)];
     __shared__ double Wd[NB_INNER * WD_LD];
     NGT_CLK(0);
@@ -320,16 +488,23 @@ panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const in
             const double sum = (u < nbp) ? rowsum[i] : 1.0;   // padding rows behave like isolated absorbing nodes
             const double t = (u < nbp && lane < nbp && lane != u) ? M[(long long)(j + u) * F.ld + j + lane] : 0.0;
             Xs[u][lane] = t;
+#ifdef NGT_OLD_GJ
             if (lane == 0) Ss[u] = sum;
             if (u == 0) {                       // first pivot, summed directly
                 const double d0 = warp_sum(t) + sum;
                 if (lane == 0) D0 = d0;
             }
+#else
+            if (lane < GJ_LD - NB_INNER) Xs[u][NB_INNER + lane] = (lane == 0) ? sum : 0.0;
+#endif
         }
     }
     __syncthreads();
     NGT_CLK(1);
 
+#ifndef NGT_OLD_GJ
+    if (crank == 0 && warp < GJ_WARPS) gj_blocked(&Xs[0][0], Wb8, nbp, errflag, warp, lane);
+#else
     if (crank == 0 && warp < GJ_WARPS) {
         const int c0 = warp * GJ_COLS;
         double X[GJ_COLS];
@@ -405,6 +580,7 @@ panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const in
 #pragma unroll
         for (int i = 0; i < GJ_COLS; ++i) Xs[lane][c0 + i] = (c0 + i < nbp) ? X[i] * RD : 0.0;
     }
+#endif
     __syncthreads();
     NGT_CLK(3);
     double *Wout = wbuf + ((long long)blockIdx.y * maxfb + slot + ko.wslot) * (NB_INNER * NB_INNER);
@@ -930,7 +1106,11 @@ int update_tile_m(int gemm_path) { return gemm_path == 1 ? FT : TM; }
 int update_tile_n(int gemm_path) { return gemm_path == 1 ? FT : TN; }
 int update_tile_k() { return TK; }
 
+__global__ void dense_network_kernel(const double *K, int n, const int *node_at, int k, double *pool, long long pool_stride,
+                                     DFront F0, DFront RF, double *tau0, int *errflag);
+
 void init_kernel_attributes() {
+    cudaFuncSetAttribute(dense_network_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_network_smem(DENSE_NET_MAX_N));
     cudaFuncSetAttribute(update_dmma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)((size_t)TSTG * TSTAGE_DOUBLES * sizeof(double)));
     cudaFuncSetAttribute(update_dmma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -978,7 +1158,7 @@ ingest_sparse_kernel(double *pool, long long pool_stride, const double *k, long 
     const double tau = 1.0 / s;
     if (lane == 0) {
         if (!(s > 0.0) || isinf(tau)) atomicOr(errflag, 2);
-        const int u = row_node[row];
+        const int u = row_node ? row_node[row] : row;     // null: every node is a row (device-built slot table)
         tau0[b * tau0_stride + u] = tau;
         if (tau_dest[row] >= 0) P[tau_dest[row]] = tau;
     }
@@ -994,6 +1174,52 @@ void launch_ingest_sparse(double *pool, long long pool_stride, int nbatch, const
     dim3 grid((n_rows + 7) / 8, nbatch);
     ingest_sparse_kernel<<<grid, 256, 0, s>>>(pool, pool_stride, k, k_stride, n_rows, row_ptr, row_node, korig, dest,
                                              tau_dest, tau0, tau0_stride, errflag);
+}
+
+// Rate -> front-slot table built on the device (networks without duplicate rates, absent or pruned nodes; the host
+// builds the table otherwise).  CSR by source node as produced by the host's edge index: row u = node u, slot q holds
+// entry korig[q].  dest[q] = pool offset of P[u][v] inside the front that owns the earlier of the two nodes;
+// tau_dest[u] = the tau slot of u's own row.  One warp per source node.
+__device__ __forceinline__ int slot_local_index(const DFront &F, int first, const int *idx, int p) {
+    if (F.k > 0 && p >= first && p < first + F.k) return p - first;
+    int lo = 0, hi = F.f - F.k;                     // update set: ascending elimination positions
+    const int *b = idx + F.k;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (b[mid] < p) lo = mid + 1; else hi = mid; }
+    return (lo < F.f - F.k && b[lo] == p) ? F.k + lo : -1;
+}
+
+__global__ void __launch_bounds__(256)
+slot_table_kernel(int n, const long long *row_ptr, const int *korig, const long long *dst, const int *pos,
+                  const int *pos_front, const DFront *fronts, const int *ffirst, const int *fidx, const long long *idx_off,
+                  long long *dest, long long *tau_dest, int *errflag) {
+    const int u = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (u >= n) return;
+    const int pu = pos[u];
+    if (lane == 0) {
+        const int owner = pos_front[pu];
+        const DFront F = fronts[owner];
+        const int lr = slot_local_index(F, ffirst[owner], fidx + idx_off[owner], pu);
+        if (lr < 0) atomicOr(errflag, 4);
+        tau_dest[u] = F.off + (long long)lr * F.ld + F.f;
+    }
+    for (long long q = row_ptr[u] + lane; q < row_ptr[u + 1]; q += 32) {
+        const int pv = pos[dst[korig[q]]];
+        const int owner = pos_front[min(pu, pv)];
+        const DFront F = fronts[owner];
+        const int *idx = fidx + idx_off[owner];
+        const int lr = slot_local_index(F, ffirst[owner], idx, pu), lc = slot_local_index(F, ffirst[owner], idx, pv);
+        if (lr < 0 || lc < 0) atomicOr(errflag, 4);
+        dest[q] = F.off + (long long)lr * F.ld + lc;
+    }
+}
+
+void launch_slot_table(int n, const long long *row_ptr, const int *korig, const long long *dst, const int *pos,
+                       const int *pos_front, const DFront *fronts, const int *ffirst, const int *fidx,
+                       const long long *idx_off, long long *dest, long long *tau_dest, int *errflag, cudaStream_t s) {
+    if (n <= 0) return;
+    slot_table_kernel<<<(n + 7) / 8, 256, 0, s>>>(n, row_ptr, korig, dst, pos, pos_front, fronts, ffirst, fidx, idx_off, dest,
+                                                 tau_dest, errflag);
 }
 
 // dense: one CTA per row of K.  Front 0 holds every intermediate (+ A ∪ B as its update set); entries between two
@@ -1038,6 +1264,164 @@ void launch_ingest_dense(double *pool, long long pool_stride, int nbatch, const 
                          int nI, DFront f0, DFront root, double *tau0, int *errflag, cudaStream_t s) {
     dim3 grid(n, nbatch);
     ingest_dense_kernel<<<grid, 256, 0, s>>>(pool, pool_stride, K, n, pos, nI, f0, root, tau0, errflag);
+}
+
+// =====================================================================================================
+// Whole-network kernel for batches of small complete networks (BASELINE config 5: thousands of 256-node networks of a
+// temperature sweep).  ONE CTA eliminates ONE network, row block by row block ("up-looking"): a block of 32 rows is
+// read from the rate matrix K straight into shared memory (tau = 1 / row sum, P = k tau: the ingest step is fused),
+// receives the updates of every earlier pivot block J,
+//     R[:, c] += R[:, X_J] U'_J[X_J, c]        c right of X_J            (FP64 DMMA; U'_J comes back from L2)
+// in order -- after link J the block's own columns X_{J+1} are final and become the A operand of link J+1 -- and is
+// then either a pivot block itself (row sums -> blocked Gauss-Jordan -> U' = W R, written to the front for the later
+// blocks and for the back-substitution) or a block of kept rows (A ∪ B), which is the reduced graph and goes straight
+// to the root front.  HBM traffic: K once in, the factor rows once out -- the right-looking multi-kernel path streams
+// every front through HBM once per 32 pivots (8 x for a 256-node network).  Same arithmetic (sums of non-negative
+// products, GTH pivots) in a different order.
+// =====================================================================================================
+constexpr int DN_THREADS = 256, DN_WARPS = DN_THREADS / 32;
+
+__host__ __device__ inline int dense_net_ldr(int n) {      // row stride of the row block: >= n + 8 and = 4 mod 16
+    int ld = n + 8;
+    return ld + ((4 - (ld & 15)) & 15);
+}
+size_t dense_network_smem(int n) {
+    return ((size_t)NB_INNER * dense_net_ldr(n) + NB_INNER * GJ_LD + 8 * WB_LD + NB_INNER) * sizeof(double) + (size_t)n * sizeof(int);
+}
+
+__global__ void __launch_bounds__(DN_THREADS, 2)
+dense_network_kernel(const double *K, int n, const int *node_at, int k, double *pool, long long pool_stride, DFront F0,
+                     DFront RF, double *tau0, int *errflag) {
+    extern __shared__ double smem[];
+    const int LDR = dense_net_ldr(n);
+    double *R = smem;                                 // NB_INNER x LDR: the current row block (column n = tau)
+    double *Xs = R + NB_INNER * LDR;                  // NB_INNER x GJ_LD: T | s  ->  W
+    double *Wb8 = Xs + NB_INNER * GJ_LD;
+    double *ssum = Wb8 + 8 * WB_LD;                   // NB_INNER row sums
+    int *nat = reinterpret_cast<int *>(ssum + NB_INNER);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    const long long b = blockIdx.x;
+    const double *Kb = K + b * (long long)n * n;
+    double *M = pool + b * pool_stride + F0.off;      // front 0: pivots 0..k-1, then the kept nodes
+    double *root = pool + b * pool_stride + RF.off;
+    const long long ld = F0.ld;
+    const int f = n;                                  // order of front 0; column f carries tau
+    for (int i = threadIdx.x; i < n; i += DN_THREADS) nat[i] = node_at[i];
+    __syncthreads();
+
+    const int npiv_blocks = (k + NB_INNER - 1) / NB_INNER;
+    const int nupd_blocks = (f - k + NB_INNER - 1) / NB_INNER;
+    for (int blk = 0; blk < npiv_blocks + nupd_blocks; ++blk) {
+        const bool is_pivot = blk < npiv_blocks;
+        const int p0 = is_pivot ? blk * NB_INNER : k + (blk - npiv_blocks) * NB_INNER;     // first elimination position
+        const int cnt = min(NB_INNER, (is_pivot ? k : f) - p0);
+        // ---- ingest: rows of K in elimination order, columns permuted the same way; tau = 1 / row sum --------------
+        for (int r = warp; r < NB_INNER; r += DN_WARPS) {
+            double *row = R + r * LDR;
+            if (r < cnt) {
+                const int u = nat[p0 + r];
+                const double *kr = Kb + (long long)u * n;
+                double s = 0.0;
+                for (int c = lane; c < n; c += 32) { const double v = kr[nat[c]]; row[c] = v; s += v; }
+                s = warp_sum(s);
+                const double tau = 1.0 / s;
+                for (int c = lane; c < n; c += 32) row[c] *= tau;
+                for (int c = n + 1 + lane; c < LDR; c += 32) row[c] = 0.0;
+                if (lane == 0) {
+                    row[n] = tau;
+                    tau0[b * n + u] = tau;
+                    if (!(s > 0.0) || isinf(tau)) atomicOr(errflag, 2);
+                }
+            } else {
+                for (int c = lane; c < LDR; c += 32) row[c] = 0.0;
+            }
+        }
+        __syncthreads();
+        // ---- links: the updates of the earlier pivot blocks, in order -------------------------------------------------
+        const int nlinks = is_pivot ? blk : npiv_blocks;
+        for (int J = 0; J < nlinks; ++J) {
+            const int jJ = J * NB_INNER, nbJ = min(NB_INNER, k - jJ), jeJ = jJ + nbJ;
+            const double *UJ = M + (long long)jJ * ld;            // U'_J rows (written earlier by this CTA; read through L2)
+            for (int tile = jeJ / 8 + warp; tile <= f / 8; tile += DN_WARPS) {
+                const int colb = tile * 8 + g;
+                double bf[NB_INNER / 4];
+#pragma unroll
+                for (int k4 = 0; k4 < NB_INNER / 4; ++k4) {
+                    const int kk = k4 * 4 + t4;
+                    bf[k4] = (kk < nbJ && colb >= jeJ && colb <= f) ? __ldcg(UJ + (long long)kk * ld + colb) : 0.0;
+                }
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    double *row = R + (mi * 8 + g) * LDR;
+                    double c0 = row[tile * 8 + 2 * t4], c1 = row[tile * 8 + 2 * t4 + 1];
+#pragma unroll
+                    for (int k4 = 0; k4 < NB_INNER / 4; ++k4) {
+                        const int kk = k4 * 4 + t4;
+                        const double a = kk < nbJ ? row[jJ + kk] : 0.0;
+                        dmma884(c0, c1, a, bf[k4]);
+                    }
+                    row[tile * 8 + 2 * t4] = c0;
+                    row[tile * 8 + 2 * t4 + 1] = c1;
+                }
+            }
+            __syncthreads();                                      // the next link's A operand is final now
+        }
+        if (is_pivot) {
+            const int j = p0, nbp = cnt, je = j + nbp;
+            // ---- mass leaving the panel (GTH row sums) and the T block -------------------------------------------------
+            for (int r = warp; r < NB_INNER; r += DN_WARPS) {
+                double sacc = 0.0;
+                if (r < nbp)
+                    for (int c = je + lane; c < f; c += 32) sacc += R[r * LDR + c];
+                sacc = warp_sum(sacc);
+                if (lane == 0) ssum[r] = (r < nbp) ? sacc : 1.0;   // padding rows behave like isolated absorbing nodes
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < NB_INNER * GJ_LD; i += DN_THREADS) {
+                const int r = i / GJ_LD, q = i % GJ_LD;
+                double v = 0.0;
+                if (q < NB_INNER) { if (r < nbp && q < nbp && q != r) v = R[r * LDR + j + q]; }
+                else if (q == NB_INNER) v = ssum[r];
+                Xs[i] = v;
+            }
+            __syncthreads();
+            if (warp < GJ_WARPS) gj_blocked(Xs, Wb8, nbp, errflag, warp, lane);
+            __syncthreads();
+            // ---- U' = W [P_XR | tau_X]: kept in the front for the later blocks and the back-substitution ----------------
+            for (int tile = je / 8 + warp; tile <= f / 8; tile += DN_WARPS) {
+                const int colb = tile * 8 + g;
+                double bf[NB_INNER / 4];
+#pragma unroll
+                for (int k4 = 0; k4 < NB_INNER / 4; ++k4) bf[k4] = R[(k4 * 4 + t4) * LDR + colb];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int k4 = 0; k4 < NB_INNER / 4; ++k4) dmma884(c0, c1, Xs[(mi * 8 + g) * GJ_LD + k4 * 4 + t4], bf[k4]);
+                    const int r = mi * 8 + g, cc = tile * 8 + 2 * t4;
+                    if (r < nbp) {
+                        double *out = M + (long long)(j + r) * ld;
+                        if (cc >= je && cc <= f) out[cc] = c0;
+                        if (cc + 1 >= je && cc + 1 <= f) out[cc + 1] = c1;
+                    }
+                }
+            }
+        } else {
+            // ---- kept rows: the reduced graph on A ∪ B, with the full tau' in the last column ---------------------------
+            const int mcols = f - k + 1;
+            for (int i = threadIdx.x; i < cnt * mcols; i += DN_THREADS) {
+                const int r = i / mcols, c = i % mcols;
+                root[(long long)(p0 - k + r) * RF.ld + c] = R[r * LDR + k + c];
+            }
+        }
+        __syncthreads();                                          // R is reloaded by the next block
+    }
+}
+
+void launch_dense_network(const double *K, int n, int nbatch, const int *node_at, int k, double *pool, long long pool_stride,
+                          DFront F0, DFront RF, double *tau0, int *errflag, cudaStream_t s) {
+    dense_network_kernel<<<nbatch, DN_THREADS, dense_network_smem(n), s>>>(K, n, node_at, k, pool, pool_stride, F0, RF, tau0,
+                                                                          errflag);
 }
 
 // =====================================================================================================

@@ -145,10 +145,23 @@ void launch_ingest_sparse(double *pool, long long pool_stride, int nbatch, const
                           int n_rows, const long long *row_ptr, const int *row_node, const int *korig,
                           const long long *dest, const long long *tau_dest, double *tau0, long long tau0_stride,
                           int *errflag, cudaStream_t s);
+// rate -> slot table on the device (see kernels.cu): row_ptr / korig = the host's CSR-by-source edge index (row u =
+// node u), dst = the caller's destination ids, pos / pos_front / ffirst / fidx / idx_off = the analysed structure
+void launch_slot_table(int n, const long long *row_ptr, const int *korig, const long long *dst, const int *pos,
+                       const int *pos_front, const DFront *fronts, const int *ffirst, const int *fidx,
+                       const long long *idx_off, long long *dest, long long *tau_dest, int *errflag, cudaStream_t s);
 // dense: K is nbatch x n x n row-major; pos = node -> elimination position; front 0 = all intermediates (k0 = nI),
 // root = last front
 void launch_ingest_dense(double *pool, long long pool_stride, int nbatch, const double *K, int n, const int *pos,
                          int nI, DFront f0, DFront root, double *tau0, int *errflag, cudaStream_t s);
+
+// ---- whole-network kernel: one CTA eliminates one small complete network (ingest + phase 1 fused; see kernels.cu) ------
+// K: nbatch x n x n rates; node_at: elimination position -> node id; k: pivots (the kept nodes follow); F0: the front of
+// all intermediates (receives the factor rows U'), RF: the root front (receives the reduced A ∪ B graph incl. tau').
+constexpr int DENSE_NET_MAX_N = 640;      // row block + Gauss-Jordan scratch of two CTAs fit one SM's shared memory up to here
+size_t dense_network_smem(int n);
+void launch_dense_network(const double *K, int n, int nbatch, const int *node_at, int k, double *pool, long long pool_stride,
+                          DFront F0, DFront RF, double *tau0, int *errflag, cudaStream_t s);
 
 // ---- assembly: child update blocks (+ delta-tau column) are added into their parents -----------------------
 // ids: parents of one tree level; row_base / row_ptr / row_child / row_crow: per parent row, the (child, child update

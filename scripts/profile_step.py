@@ -2,6 +2,8 @@
     python scripts/profile_step.py c2            # 10^5-minima landscape (bench.py's N=1 workload)
     python scripts/profile_step.py dense 8192    # complete graph
     python scripts/profile_step.py batch 256 512 # 512 complete 256-node networks
+    python scripts/profile_step.py c4            # 2*10^4-node landscape, |A|=|B|=512 (phase 2)
+    python scripts/profile_step.py c5            # the 4096 x 256-node temperature sweep of bench.py
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -22,6 +24,13 @@ a = ap.parse_args()
 if a.workload == "c2":
     n, src, dst, k, A, B = synth.landscape_2d(a.size or 316, T=0.3, seed=0)
     h = Handle.from_coo(n, src, dst, k, A, B, gemm_path=a.gemm)
+elif a.workload == "c4":
+    n, src, dst, k, A, B = synth.landscape_groups(141, 512, 512, T=0.3, seed=0)
+    h = Handle.from_coo(n, src, dst, k, A, B, gemm_path=a.gemm)
+elif a.workload == "c5":
+    import bench
+    K = bench.c5_rate_matrices(torch, 0, a.nbatch or bench.C5_NB)
+    h = Handle.from_dense(K, [0], [bench.C5_N - 1], gemm_path=a.gemm)
 elif a.workload == "dense":
     N = a.size or 8192
     K = torch.rand(N, N, dtype=torch.float64, device="cuda"); K.fill_diagonal_(0)
