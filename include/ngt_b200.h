@@ -163,6 +163,15 @@ int ngt_dist_apply(ngt_handle h, int64_t J);
 int ngt_dist_root(ngt_handle h, double **dptr, int64_t *ndoubles);
 int ngt_dist_finish(ngt_handle h);
 
+/* ---- graph validation on the device ------------------------------------------------------
+ * Connected components of the undirected structure of the rate graph (src[e] -- dst[e]) by a lock-free
+ * union-find kernel: labels[u] = smallest node id of u's component, *ncomp (may be NULL) = number of components
+ * (ids that appear in no rate are components of their own).  Replaces the networkx sweeps the reference runs
+ * before it accepts A and B (kmc_rates/_kmc_rates.py:384-454) and in reduce_rates (rates_linalg.py:13-41).
+ * Host pointers; labels has n entries. */
+int ngt_connected_components(int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, int32_t device,
+                             int32_t *labels, int64_t *ncomp);
+
 /* ---- multi-GPU, driven from C++ with NCCL on the engine's own streams --------------------------------------
  * One communicator per process and GPU.  NCCL is bound at run time (dlopen of the libnccl.so.2 the host process
  * already uses); the 128-byte unique id is made on one rank (ngt_comm_unique_id) and handed to the others by

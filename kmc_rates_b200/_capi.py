@@ -107,6 +107,7 @@ def lib():
         "ngt_dist_apply": [H, i64],
         "ngt_dist_root": [H, ctypes.POINTER(vp), _i64p],
         "ngt_dist_finish": [H],
+        "ngt_connected_components": [i64, i64, _i64p, _i64p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), _i64p],
         "ngt_comm_unique_id": [ctypes.POINTER(ctypes.c_uint8)],
         "ngt_comm_create": [ctypes.c_int32, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int32, ctypes.c_int32, HP],
         "ngt_dist_phase_one": [H, H, _f64p],
@@ -135,7 +136,7 @@ EXPORTED_SYMBOLS = [
     "ngt_get_stats", "ngt_timed_steps", "ngt_profile_schur", "ngt_batch_create", "ngt_batch_create_dense", "ngt_batch_create_dense_dev", "ngt_batch_get_rates",
     "ngt_reduced_block_dev", "ngt_phase_two_shard", "ngt_set_final", "ngt_final_dev", "ngt_adopt_final_dev", "ngt_dist_begin", "ngt_dist_info", "ngt_dist_rowsum",
     "ngt_dist_factor", "ngt_dist_panel", "ngt_dist_apply", "ngt_dist_root", "ngt_dist_finish", "ngt_trim_device_cache",
-    "ngt_comm_unique_id", "ngt_comm_create", "ngt_comm_destroy", "ngt_dist_phase_one", "ngt_phase_two_sharded",
+    "ngt_connected_components", "ngt_comm_unique_id", "ngt_comm_create", "ngt_comm_destroy", "ngt_dist_phase_one", "ngt_phase_two_sharded",
     "ngt_last_error",
     "ngt_version",
 ]
@@ -160,6 +161,20 @@ def _ids(seq):
 
 def _is_torch_cuda(x):
     return hasattr(x, "data_ptr") and hasattr(x, "is_cuda") and x.is_cuda
+
+
+def connected_components(n, src, dst, device=0):
+    """(number of components, labels) of the undirected structure of the rate graph, computed by the union-find kernel
+    (include/ngt_b200.h, ngt_connected_components); labels[u] = smallest node id of u's component."""
+    src = np.ascontiguousarray(src, np.int64)
+    dst = np.ascontiguousarray(dst, np.int64)
+    if src.size != dst.size:
+        raise ValueError("src and dst have different lengths")
+    labels = np.empty(int(n), np.int32)
+    ncomp = ctypes.c_int64()
+    check(lib().ngt_connected_components(int(n), src.size, src.ctypes.data_as(_i64p), dst.ctypes.data_as(_i64p), int(device),
+                                         labels.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.byref(ncomp)))
+    return ncomp.value, labels
 
 
 class Comm(object):

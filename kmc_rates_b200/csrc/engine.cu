@@ -2107,6 +2107,44 @@ int ngt_dist_info(ngt_handle h, int64_t *n_pivots, int64_t *block) {
     });
 }
 
+int ngt_connected_components(int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, int32_t device,
+                             int32_t *labels, int64_t *ncomp) {
+    return guard([&] {
+        if (n < 0 || nnz < 0 || (nnz > 0 && (!src || !dst)) || (n > 0 && !labels)) throw InvalidError("bad argument");
+        if (n > 2000000000LL) throw InvalidError("too many nodes (32-bit labels)");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw CudaError("no CUDA device — kmc_rates_b200 has no CPU fallback");
+        if (device < 0 || device >= ndev) throw InvalidError("device ordinal out of range");
+        CK(cudaSetDevice(device));
+        DevBuf<int> parent, err;
+        DevBuf<long long> ds, dd;
+        parent.alloc((size_t)std::max<int64_t>(n, 1));
+        err.alloc(1);
+        CK(cudaMemset(err.p, 0, sizeof(int)));
+        ds.alloc((size_t)std::max<int64_t>(nnz, 1));
+        dd.alloc((size_t)std::max<int64_t>(nnz, 1));
+        static_assert(sizeof(long long) == sizeof(int64_t), "ids are uploaded as they are");
+        if (nnz > 0) {
+            CK(cudaMemcpy(ds.p, src, (size_t)nnz * sizeof(int64_t), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(dd.p, dst, (size_t)nnz * sizeof(int64_t), cudaMemcpyHostToDevice));
+            g_h2d_bytes += (long long)nnz * 16;
+        }
+        ngt::launch_connected_components(parent.p, ds.p, dd.p, nnz, (int)n, err.p, 0);
+        CK(cudaGetLastError());
+        int flag = 0;
+        CK(cudaMemcpy(&flag, err.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (flag) throw InvalidError("rate endpoint out of range");
+        if (n > 0) CK(cudaMemcpy(labels, parent.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        g_d2h_bytes += (long long)n * 4;
+        if (ncomp) {
+            int64_t c = 0;
+            for (int64_t i = 0; i < n; ++i) c += labels[i] == (int32_t)i;
+            *ncomp = c;
+        }
+    });
+}
+
 // ---- NCCL communicator + the sharded paths driven from C++ ----------------------------------------------------
 int ngt_comm_unique_id(uint8_t id[128]) {
     return guard([&] {

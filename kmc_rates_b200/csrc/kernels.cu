@@ -216,6 +216,16 @@ __device__ __forceinline__ double gj_tail_sum(const double (&X)[GJ_COLS], int t)
 }
 __device__ __forceinline__ void gj_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(GJ_WARPS * 32) : "memory"); }
 
+#ifdef NGT_PANEL_CLOCKS
+__device__ long long g_panel_clk[8];
+__device__ long long g_gj_clk[8];
+#define NGT_CLK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_panel_clk[i] = clock64(); } while (0)
+#define NGT_GJ_T(i) do { const long long t_ = clock64(); gj_acc[i] += t_ - gj_last; gj_last = t_; } while (0)
+#else
+#define NGT_CLK(i) do { } while (0)
+#define NGT_GJ_T(i) do { } while (0)
+#endif
+
 // -----------------------------------------------------------------------------------------------------
 // Blocked subtraction-free Gauss-Jordan: W = (I - T)^-1 of a 32-pivot panel in 8-pivot blocks (4 warps).
 //   working matrix G: NB_INNER x GJ_LD in shared memory; columns 0..31 hold T (diagonal ignored), column 32 the mass s
@@ -303,10 +313,15 @@ __device__ __forceinline__ void gj_bar2_sync() { asm volatile("bar.sync 2, %0;" 
 // all GJ_WARPS warps call this convergently; G is overwritten by W (rows >= nbp zeroed), Wb is scratch (8 x WB_LD)
 __device__ __forceinline__ void gj_blocked(double *G, double *Wb, int nbp, int *errflag, int warp, int lane) {
     const int g = lane >> 2, t4 = lane & 3;
+#ifdef NGT_PANEL_CLOCKS
+    long long gj_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, gj_last = clock64();
+#endif
 #pragma unroll 1
     for (int b = 0; b < NB_INNER / 8; ++b) {
         if (warp == 0) gj8_invert(G, b, Wb, lane, errflag);
+        NGT_GJ_T(0);
         gj_barrier();                                  // W_b is visible
+        NGT_GJ_T(1);
         // this warp's column tile: one of the three other 8-column tiles of the working matrix; warp 3: the s column
         const int ct = warp < 3 ? (warp < b ? warp : warp + 1) : 4;
         // operand fragments, read before anything is overwritten
@@ -373,22 +388,19 @@ __device__ __forceinline__ void gj_blocked(double *G, double *Wb, int nbp, int *
             row[2 * t4] = Wb[g * WB_LD + 2 * t4];
             row[2 * t4 + 1] = Wb[g * WB_LD + 2 * t4 + 1];
         }
+        NGT_GJ_T(2);
         gj_barrier();                                  // step b complete (also protects W_b against the next inversion)
+        NGT_GJ_T(3);
     }
+#ifdef NGT_PANEL_CLOCKS
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        for (int i = 0; i < 8; ++i) g_gj_clk[i] = gj_acc[i];
+#endif
     // padding rows (panels with fewer than 32 pivots) were treated as isolated absorbing nodes: clear them
     for (int i = warp * 32 + lane; i < (NB_INNER - nbp) * NB_INNER; i += GJ_WARPS * 32)
         G[(nbp + i / NB_INNER) * GJ_LD + (i % NB_INNER)] = 0.0;
 }
 
-#ifdef NGT_PANEL_CLOCKS
-__device__ long long g_panel_clk[8];
-__device__ long long g_gj_clk[8];
-#define NGT_CLK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_panel_clk[i] = clock64(); } while (0)
-#define NGT_GJ_T(i) do { const long long t_ = clock64(); gj_acc[i] += t_ - gj_last; gj_last = t_; } while (0)
-#else
-#define NGT_CLK(i) do { } while (0)
-#define NGT_GJ_T(i) do { } while (0)
-#endif
 
 // CL > 1: the launch is made of thread-block clusters of CL CTAs per front (single fronts at the top of the assembly
 // tree, where the whole GPU waits on this chain): all CTAs sum one column chunk of the 32 panel rows each, CTA 0 runs
@@ -1316,24 +1328,54 @@ dense_network_kernel(const double *K, int n, const int *node_at, int k, double *
         const int p0 = is_pivot ? blk * NB_INNER : k + (blk - npiv_blocks) * NB_INNER;     // first elimination position
         const int cnt = min(NB_INNER, (is_pivot ? k : f) - p0);
         // ---- ingest: rows of K in elimination order, columns permuted the same way; tau = 1 / row sum --------------
-        for (int r = warp; r < NB_INNER; r += DN_WARPS) {
-            double *row = R + r * LDR;
-            if (r < cnt) {
-                const int u = nat[p0 + r];
-                const double *kr = Kb + (long long)u * n;
-                double s = 0.0;
-                for (int c = lane; c < n; c += 32) { const double v = kr[nat[c]]; row[c] = v; s += v; }
-                s = warp_sum(s);
-                const double tau = 1.0 / s;
-                for (int c = lane; c < n; c += 32) row[c] *= tau;
-                for (int c = n + 1 + lane; c < LDR; c += 32) row[c] = 0.0;
-                if (lane == 0) {
-                    row[n] = tau;
-                    tau0[b * n + u] = tau;
-                    if (!(s > 0.0) || isinf(tau)) atomicOr(errflag, 2);
+        // a warp owns rows warp, warp + 8, ...; the loads of all its rows are issued together (one round of memory
+        // latency per 256 columns instead of one per element)
+        {
+            constexpr int RPW = NB_INNER / DN_WARPS;
+            double s[RPW];
+            const double *kr[RPW];
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) {
+                const int r = warp + i * DN_WARPS;
+                s[i] = 0.0;
+                kr[i] = r < cnt ? Kb + (long long)nat[p0 + r] * n : nullptr;
+            }
+            for (int c0 = 0; c0 < n; c0 += 256) {
+                double v[RPW][8];
+                int src[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) { const int c = c0 + lane + 32 * jj; src[jj] = c < n ? nat[c] : -1; }
+#pragma unroll
+                for (int i = 0; i < RPW; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) v[i][jj] = (kr[i] && src[jj] >= 0) ? kr[i][src[jj]] : 0.0;
+#pragma unroll
+                for (int i = 0; i < RPW; ++i) {
+                    double *row = R + (warp + i * DN_WARPS) * LDR;
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int c = c0 + lane + 32 * jj;
+                        if (c < n) { row[c] = v[i][jj]; s[i] += v[i][jj]; }
+                    }
                 }
-            } else {
-                for (int c = lane; c < LDR; c += 32) row[c] = 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) {
+                const int r = warp + i * DN_WARPS;
+                double *row = R + r * LDR;
+                const double sum = warp_sum(s[i]);
+                if (r < cnt) {
+                    const double tau = 1.0 / sum;
+                    for (int c = lane; c < n; c += 32) row[c] *= tau;
+                    for (int c = n + 1 + lane; c < LDR; c += 32) row[c] = 0.0;
+                    if (lane == 0) {
+                        row[n] = tau;
+                        tau0[b * n + nat[p0 + r]] = tau;
+                        if (!(sum > 0.0) || isinf(tau)) atomicOr(errflag, 2);
+                    }
+                } else {
+                    for (int c = n + lane; c < LDR; c += 32) row[c] = 0.0;     // columns < n were written as zeros above
+                }
             }
         }
         __syncthreads();
@@ -1342,14 +1384,21 @@ dense_network_kernel(const double *K, int n, const int *node_at, int k, double *
         for (int J = 0; J < nlinks; ++J) {
             const int jJ = J * NB_INNER, nbJ = min(NB_INNER, k - jJ), jeJ = jJ + nbJ;
             const double *UJ = M + (long long)jJ * ld;            // U'_J rows (written earlier by this CTA; read through L2)
-            for (int tile = jeJ / 8 + warp; tile <= f / 8; tile += DN_WARPS) {
+            // B fragments (U'_J) come from L2: the next tile's are requested before the current tile is computed
+            auto load_b = [&](int tile, double (&bf)[NB_INNER / 4]) {
                 const int colb = tile * 8 + g;
-                double bf[NB_INNER / 4];
 #pragma unroll
                 for (int k4 = 0; k4 < NB_INNER / 4; ++k4) {
                     const int kk = k4 * 4 + t4;
                     bf[k4] = (kk < nbJ && colb >= jeJ && colb <= f) ? __ldcg(UJ + (long long)kk * ld + colb) : 0.0;
                 }
+            };
+            double bf[NB_INNER / 4], bn[NB_INNER / 4];
+            int tile = jeJ / 8 + warp;
+            if (tile <= f / 8) load_b(tile, bf);
+            for (; tile <= f / 8; tile += DN_WARPS) {
+                const bool more = tile + DN_WARPS <= f / 8;
+                if (more) load_b(tile + DN_WARPS, bn);
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi) {
                     double *row = R + (mi * 8 + g) * LDR;
@@ -1362,6 +1411,10 @@ dense_network_kernel(const double *K, int n, const int *node_at, int k, double *
                     }
                     row[tile * 8 + 2 * t4] = c0;
                     row[tile * 8 + 2 * t4 + 1] = c1;
+                }
+                if (more) {
+#pragma unroll
+                    for (int k4 = 0; k4 < NB_INNER / 4; ++k4) bf[k4] = bn[k4];
                 }
             }
             __syncthreads();                                      // the next link's A operand is final now
@@ -1489,7 +1542,9 @@ assemble_kernel(double *pool, long long pool_stride, const DFront *fronts, const
 }
 
 bool assemble_splits_rows(int nparents, int nbatch, int max_f) {
-    return (long long)nparents * nbatch * ((max_f + 7) / 8) < 4 * 148;
+    // few parents, or long rows: a single warp walking a row of ~1000 columns is a chain of dependent gathers, and the
+    // mid-tree levels (tens of parents) were bound by that latency, not by bandwidth
+    return (long long)nparents * nbatch * ((max_f + 7) / 8) < 4 * 148 || max_f >= 384;
 }
 
 void launch_assemble(const LaunchCtx &c, const int *ids, int nparents, int max_f, const long long *row_base,
@@ -1682,6 +1737,59 @@ void launch_dist_root_contrib(const double *M, int ld, int f, int nI, int m, KOp
 void launch_dist_root_finish(double *root, int ld_root, int m, const double *contrib, const double *tau_glob, int nI,
                              cudaStream_t s) {
     dist_root_finish_kernel<<<(m * (m + 1) + 255) / 256, 256, 0, s>>>(root, ld_root, m, contrib, tau_glob, nI);
+}
+
+// =====================================================================================================
+// Graph validation on the device: connected components of the undirected structure of the rate graph
+// by a lock-free union-find -- what the reference does with networkx sweeps before it accepts A and B (reference
+// kmc_rates/_kmc_rates.py:384-454) and when it drops rates that cannot reach B (rates_linalg.py:13-41).
+// Roots are always hooked towards the smaller id, so a component's label is its smallest node id (deterministic).
+// =====================================================================================================
+__device__ __forceinline__ int cc_find(int *parent, int x) {
+    int p = parent[x];
+    while (p != x) {                       // path halving; concurrent writers only ever move entries closer to the root
+        const int gp = parent[p];
+        if (gp != p) parent[x] = gp;
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+
+__global__ void cc_init_kernel(int *parent, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) parent[i] = i;
+}
+
+__global__ void cc_hook_kernel(int *parent, const long long *src, const long long *dst, long long nnz, int n, int *errflag) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const long long u0 = src[e], v0 = dst[e];
+    if (u0 < 0 || u0 >= n || v0 < 0 || v0 >= n) { atomicOr(errflag, 8); return; }
+    int u = (int)u0, v = (int)v0;
+    while (true) {
+        u = cc_find(parent, u);
+        v = cc_find(parent, v);
+        if (u == v) break;
+        const int hi = max(u, v), lo = min(u, v);
+        const int old = atomicCAS(parent + hi, hi, lo);      // hook the larger root under the smaller one
+        if (old == hi) break;
+        u = old;                                             // somebody else moved hi first: continue from there
+        v = lo;
+    }
+}
+
+__global__ void cc_flatten_kernel(int *parent, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) parent[i] = cc_find(parent, i);
+}
+
+void launch_connected_components(int *parent, const long long *src, const long long *dst, long long nnz, int n, int *errflag,
+                                 cudaStream_t s) {
+    if (n <= 0) return;
+    cc_init_kernel<<<(n + 255) / 256, 256, 0, s>>>(parent, n);
+    if (nnz > 0) cc_hook_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(parent, src, dst, nnz, n, errflag);
+    cc_flatten_kernel<<<(n + 255) / 256, 256, 0, s>>>(parent, n);
 }
 
 // =====================================================================================================

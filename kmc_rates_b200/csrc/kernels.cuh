@@ -202,6 +202,10 @@ void launch_dist_root_contrib(const double *M, int ld, int f, int nI, int m, KOp
 void launch_dist_root_finish(double *root, int ld_root, int m, const double *contrib, const double *tau_glob, int nI,
                              cudaStream_t s);
 
+// ---- graph validation: connected components (label = smallest node id of the component) ---------------------
+void launch_connected_components(int *parent, const long long *src, const long long *dst, long long nnz, int n, int *errflag,
+                                 cudaStream_t s);
+
 // ---- committor / MFPT back-substitution over kept factors -------------------------------------------
 // x is nbatch x npos x 2 (q, t interleaved) indexed by elimination position; one call handles the panel that
 // starts at pivot j of every front in `ids`; the host sweeps levels top-down and panels in reverse.

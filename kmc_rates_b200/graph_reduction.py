@@ -1,16 +1,15 @@
 """`GraphReduction` and `kmcgraph_from_rates`: drop-in for the reference's exported Python API
 (reference kmc_rates/_kmc_rates.py, kmc_rates/__init__.py:1-3), with the arithmetic on B200.
 
-What stays on the host (as in the reference): label handling, input validation, pruning of components that
-touch neither A nor B (reference _kmc_rates.py:384-454), and the final weighted averages.  What moves to the
-GPU: every P / tau update (reference _kmc_rates.py:274-355), phase 1, phase 2 and the committor solves.
+What stays on the host (as in the reference): label handling, the per-node sanity checks and the final weighted
+averages.  What moves to the GPU: every P / tau update (reference _kmc_rates.py:274-355), phase 1, phase 2, the
+committor solves, and the connectivity analysis behind the A / B checks and the pruning of components that touch
+neither A nor B (reference _kmc_rates.py:384-454; a union-find kernel, `_capi.connected_components`).
 """
 from collections import defaultdict
 
 import networkx as nx
 import numpy as np
-import scipy.sparse
-import scipy.sparse.csgraph
 
 from . import _capi
 from .ngt import _label_maps, rates_to_coo
@@ -248,8 +247,8 @@ class GraphReduction(object):
             raise ValueError("A and B have at least one node in common")
         n = len(labels)
         src, dst, _k = rates_to_coo(self._rates, labels)
-        adj = scipy.sparse.coo_matrix((np.ones(src.size), (src, dst)), shape=(n, n))
-        ncomp, comp = scipy.sparse.csgraph.connected_components(adj, directed=False)
+        # connected components by the union-find kernel (the reference sweeps the graph with networkx, :384-454)
+        ncomp, comp = _capi.connected_components(n, src, dst, device=self._opt["device"])
         if ncomp != 1:
             self._check_A_B_connected(labels, comp)
             self._graph = None

@@ -12,8 +12,6 @@ Same constructor, methods, attributes (`mfptimes`, `committor_dict`, `sum_out_ra
 from collections import defaultdict
 
 import numpy as np
-import scipy.sparse
-import scipy.sparse.csgraph
 
 from . import _capi
 from .ngt import _label_maps, rates_to_coo
@@ -23,7 +21,7 @@ class LinalgError(Exception):
     """raised when a solve returns unphysical values"""
 
 
-def reduce_rates(rates, B, A=None):
+def reduce_rates(rates, B, A=None, device=0):
     """drop every rate whose tail is not connected to B (reference rates_linalg.py:13-41)"""
     B = set(B)
     if A is not None:
@@ -33,8 +31,7 @@ def reduce_rates(rates, B, A=None):
     labels = _label_maps(rates)
     n = len(labels)
     src, dst, _k = rates_to_coo(rates, labels)
-    adj = scipy.sparse.coo_matrix((np.ones(src.size), (src, dst)), shape=(n, n))
-    _nc, comp = scipy.sparse.csgraph.connected_components(adj, directed=False)
+    _nc, comp = _capi.connected_components(n, src, dst, device=device)      # union-find kernel
     good = comp[labels[next(iter(B))]]
     connected = {u for u, i in labels.items() if comp[i] == good}
     if len(connected) != n:
@@ -59,7 +56,7 @@ class TwoStateRates(object):
 
     def __init__(self, rate_constants, A, B, weights=None, check_rates=True, device=0):
         if check_rates:
-            self.rate_constants = reduce_rates(rate_constants, B, A=A)
+            self.rate_constants = reduce_rates(rate_constants, B, A=A, device=device)
         else:
             self.rate_constants = rate_constants
         self.A = A

@@ -217,3 +217,25 @@ def test_two_state_rates_with_absorbing_product_nodes():
     for u in labels:
         if u not in A and u not in B:
             assert abs(twin.get_committor(u) - la.q[idx[u]]) < 1e-9
+
+
+def test_connected_components_kernel_matches_scipy():
+    """graph validation on the device: union-find labels against scipy's connected components"""
+    import scipy.sparse
+    import scipy.sparse.csgraph
+    from kmc_rates_b200 import _capi
+    rng = np.random.default_rng(7)
+    for n, nnz in [(1, 0), (5, 0), (50, 30), (2000, 1500), (20000, 60000), (300000, 280000)]:
+        src = rng.integers(0, n, nnz)
+        dst = rng.integers(0, n, nnz)
+        nc, lab = _capi.connected_components(n, src, dst)
+        adj = scipy.sparse.coo_matrix((np.ones(nnz), (src, dst)), shape=(n, n))
+        nc_ref, lab_ref = scipy.sparse.csgraph.connected_components(adj, directed=False)
+        assert nc == nc_ref
+        # same partition, and the label is the smallest member
+        first = {}
+        for u, l in enumerate(lab_ref):
+            first.setdefault(l, u)
+        assert np.array_equal(lab, np.array([first[l] for l in lab_ref], np.int32))
+    with pytest.raises(ValueError):
+        _capi.connected_components(4, [0, 5], [1, 2])
