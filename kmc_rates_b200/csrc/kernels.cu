@@ -1292,6 +1292,11 @@ void launch_ingest_dense(double *pool, long long pool_stride, int nbatch, const 
 // products, GTH pivots) in a different order.
 // =====================================================================================================
 constexpr int DN_THREADS = 256, DN_WARPS = DN_THREADS / 32;
+#ifdef NGT_DN_CLOCKS   // phase split of one CTA (printed by block 0): scripts/build_variant.sh dnclk -DNGT_DN_CLOCKS
+#define DN_T(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); dn_acc[i] += t_ - dn_last; dn_last = t_; } } while (0)
+#else
+#define DN_T(i) do { } while (0)
+#endif
 
 __host__ __device__ inline int dense_net_ldr(int n) {      // row stride of the row block: >= n + 8 and = 4 mod 16
     int ld = n + 8;
@@ -1320,6 +1325,9 @@ dense_network_kernel(const double *K, int n, const int *node_at, int k, double *
     const int f = n;                                  // order of front 0; column f carries tau
     for (int i = threadIdx.x; i < n; i += DN_THREADS) nat[i] = node_at[i];
     __syncthreads();
+#ifdef NGT_DN_CLOCKS
+    long long dn_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dn_last = clock64();
+#endif
 
     const int npiv_blocks = (k + NB_INNER - 1) / NB_INNER;
     const int nupd_blocks = (f - k + NB_INNER - 1) / NB_INNER;
@@ -1379,6 +1387,7 @@ dense_network_kernel(const double *K, int n, const int *node_at, int k, double *
             }
         }
         __syncthreads();
+        DN_T(0);
         // ---- links: the updates of the earlier pivot blocks, in order -------------------------------------------------
         const int nlinks = is_pivot ? blk : npiv_blocks;
         for (int J = 0; J < nlinks; ++J) {
@@ -1419,6 +1428,7 @@ dense_network_kernel(const double *K, int n, const int *node_at, int k, double *
             }
             __syncthreads();                                      // the next link's A operand is final now
         }
+        DN_T(1);
         if (is_pivot) {
             const int j = p0, nbp = cnt, je = j + nbp;
             // ---- mass leaving the panel (GTH row sums) and the T block -------------------------------------------------
@@ -1438,8 +1448,10 @@ dense_network_kernel(const double *K, int n, const int *node_at, int k, double *
                 Xs[i] = v;
             }
             __syncthreads();
+            DN_T(2);
             if (warp < GJ_WARPS) gj_blocked(Xs, Wb8, nbp, errflag, warp, lane);
             __syncthreads();
+            DN_T(3);
             // ---- U' = W [P_XR | tau_X]: kept in the front for the later blocks and the back-substitution ----------------
             for (int tile = je / 8 + warp; tile <= f / 8; tile += DN_WARPS) {
                 const int colb = tile * 8 + g;
@@ -1468,7 +1480,13 @@ dense_network_kernel(const double *K, int n, const int *node_at, int k, double *
             }
         }
         __syncthreads();                                          // R is reloaded by the next block
+        DN_T(4);
     }
+#ifdef NGT_DN_CLOCKS
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        printf("dense_network_kernel clocks (CTA 0): ingest %lld  links %lld  rowsum+T %lld  gauss-jordan %lld  U'/root %lld\n",
+               dn_acc[0], dn_acc[1], dn_acc[2], dn_acc[3], dn_acc[4]);
+#endif
 }
 
 void launch_dense_network(const double *K, int n, int nbatch, const int *node_at, int k, double *pool, long long pool_stride,
@@ -1542,9 +1560,9 @@ assemble_kernel(double *pool, long long pool_stride, const DFront *fronts, const
 }
 
 bool assemble_splits_rows(int nparents, int nbatch, int max_f) {
-    // few parents, or long rows: a single warp walking a row of ~1000 columns is a chain of dependent gathers, and the
-    // mid-tree levels (tens of parents) were bound by that latency, not by bandwidth
-    return (long long)nparents * nbatch * ((max_f + 7) / 8) < 4 * 148 || max_f >= 384;
+    // only levels with a handful of parents: with tens of parents the extra warps per row cost more than they hide
+    // (measured on the 10^5-minima landscape: 0.60 -> 0.69 ms when rows of >= 384 columns were split as well)
+    return (long long)nparents * nbatch * ((max_f + 7) / 8) < 4 * 148;
 }
 
 void launch_assemble(const LaunchCtx &c, const int *ids, int nparents, int max_f, const long long *row_base,
@@ -1779,9 +1797,14 @@ __global__ void cc_hook_kernel(int *parent, const long long *src, const long lon
     }
 }
 
+// every entry is rewritten by its own thread only (a halving write of another thread could otherwise put an old
+// ancestor back over a freshly written root); readers see either the old ancestor or the root, both lead to the root
 __global__ void cc_flatten_kernel(int *parent, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) parent[i] = cc_find(parent, i);
+    if (i >= n) return;
+    int r = i;
+    for (int p = parent[r]; p != r; p = parent[r]) r = p;
+    parent[i] = r;
 }
 
 void launch_connected_components(int *parent, const long long *src, const long long *dst, long long nnz, int n, int *errflag,
