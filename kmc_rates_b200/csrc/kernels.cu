@@ -274,7 +274,10 @@ __device__ __forceinline__ void gj8_invert(const double *G, int b, double *Wb, i
     double dcur = __shfl_sync(FULL, gj8_tail(x0, x1, cg, 1) + sg, 0);
     double rd = 1.0 / dcur;
     bool bad = false;
-#pragma unroll
+    // NOT unrolled: the eight steps unrolled are ~11 KB of straight-line code that a single warp runs once per block --
+    // measured instruction-fetch bound (3x slower inside the whole-network kernel, whose loop body no longer fit the
+    // instruction cache); the rolled loop costs a few integer instructions per step
+#pragma unroll 1
     for (int p = 0; p < 8; ++p) {
         bad = bad || !(dcur > 0.0) || isinf(dcur);
         const double xp0 = __shfl_sync(FULL, x0, p + 8 * cg), xp1 = __shfl_sync(FULL, x1, p + 8 * cg);
@@ -1340,6 +1343,7 @@ dense_network_kernel(const double *K, int n, const int *node_at, int k, double *
         // latency per 256 columns instead of one per element)
         {
             constexpr int RPW = NB_INNER / DN_WARPS;
+            static_assert(RPW == 4, "row sums are selected by hand below");
             double s[RPW];
             const double *kr[RPW];
 #pragma unroll
@@ -1367,11 +1371,11 @@ dense_network_kernel(const double *K, int n, const int *node_at, int k, double *
                     }
                 }
             }
-#pragma unroll
+#pragma unroll 1
             for (int i = 0; i < RPW; ++i) {
                 const int r = warp + i * DN_WARPS;
                 double *row = R + r * LDR;
-                const double sum = warp_sum(s[i]);
+                const double sum = warp_sum(i == 0 ? s[0] : i == 1 ? s[1] : i == 2 ? s[2] : s[3]);
                 if (r < cnt) {
                     const double tau = 1.0 / sum;
                     for (int c = lane; c < n; c += 32) row[c] *= tau;
