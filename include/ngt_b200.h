@@ -172,6 +172,19 @@ int ngt_dist_finish(ngt_handle h);
 int ngt_connected_components(int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, int32_t device,
                              int32_t *labels, int64_t *ncomp);
 
+/* ---- PATHSAMPLE ingest on the device (reference kmc_rates/utils.py:29-95) ---------------------
+ * Rate constants of a min.data / ts.data database: mindata is nmin x 3 (energy, fvib, point-group order), tsdata
+ * nts x 3 (the same for the transition states), m1 / m2 the 0-based minima each transition state joins, T the
+ * temperature.  Both directions of every transition state are evaluated in log space, shifted by the largest log
+ * rate (returned in *log_rate_subtracted; rate_norm = exp(-that)), transition states between the same ordered
+ * pair summed (log-sum-exp), self-connecting ones dropped.  Output: *n_out directed rates src[i] -> dst[i] (0-based,
+ * sorted by (src, dst)) with rate constants k[i]; the three arrays must hold 2*nts entries.  Host pointers.
+ * Errors are reported through ngt_pathsample_last_error(). */
+int ngt_pathsample_rates(int64_t nmin, int64_t nts, const double *mindata, const double *tsdata, const int64_t *m1,
+                         const int64_t *m2, double T, int32_t device, int64_t *n_out, int64_t *src, int64_t *dst,
+                         double *k, double *log_rate_subtracted);
+const char *ngt_pathsample_last_error(void);
+
 /* ---- multi-GPU, driven from C++ with NCCL on the engine's own streams --------------------------------------
  * One communicator per process and GPU.  NCCL is bound at run time (dlopen of the libnccl.so.2 the host process
  * already uses); the 128-byte unique id is made on one rank (ngt_comm_unique_id) and handed to the others by

@@ -108,6 +108,8 @@ def lib():
         "ngt_dist_root": [H, ctypes.POINTER(vp), _i64p],
         "ngt_dist_finish": [H],
         "ngt_connected_components": [i64, i64, _i64p, _i64p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), _i64p],
+        "ngt_pathsample_rates": [i64, i64, _f64p, _f64p, _i64p, _i64p, ctypes.c_double, ctypes.c_int32, _i64p, _i64p, _i64p,
+                                 _f64p, _f64p],
         "ngt_comm_unique_id": [ctypes.POINTER(ctypes.c_uint8)],
         "ngt_comm_create": [ctypes.c_int32, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int32, ctypes.c_int32, HP],
         "ngt_dist_phase_one": [H, H, _f64p],
@@ -124,6 +126,7 @@ def lib():
     L.ngt_trim_device_cache.argtypes = []
     L.ngt_trim_device_cache.restype = None
     L.ngt_last_error.restype = ctypes.c_char_p
+    L.ngt_pathsample_last_error.restype = ctypes.c_char_p
     L.ngt_version.restype = ctypes.c_char_p
     _lib = L
     return L
@@ -136,7 +139,7 @@ EXPORTED_SYMBOLS = [
     "ngt_get_stats", "ngt_timed_steps", "ngt_profile_schur", "ngt_batch_create", "ngt_batch_create_dense", "ngt_batch_create_dense_dev", "ngt_batch_get_rates",
     "ngt_reduced_block_dev", "ngt_phase_two_shard", "ngt_set_final", "ngt_final_dev", "ngt_adopt_final_dev", "ngt_dist_begin", "ngt_dist_info", "ngt_dist_rowsum",
     "ngt_dist_factor", "ngt_dist_panel", "ngt_dist_apply", "ngt_dist_root", "ngt_dist_finish", "ngt_trim_device_cache",
-    "ngt_connected_components", "ngt_comm_unique_id", "ngt_comm_create", "ngt_comm_destroy", "ngt_dist_phase_one", "ngt_phase_two_sharded",
+    "ngt_connected_components", "ngt_pathsample_rates", "ngt_pathsample_last_error", "ngt_comm_unique_id", "ngt_comm_create", "ngt_comm_destroy", "ngt_dist_phase_one", "ngt_phase_two_sharded",
     "ngt_last_error",
     "ngt_version",
 ]
@@ -175,6 +178,29 @@ def connected_components(n, src, dst, device=0):
     check(lib().ngt_connected_components(int(n), src.size, src.ctypes.data_as(_i64p), dst.ctypes.data_as(_i64p), int(device),
                                          labels.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.byref(ncomp)))
     return ncomp.value, labels
+
+
+def pathsample_rates(mindata, tsdata, m1, m2, T, device=0):
+    """PATHSAMPLE rate constants on the device (include/ngt_b200.h, ngt_pathsample_rates): returns
+    (src, dst, k, log_rate_subtracted) with 0-based minima, sorted by (src, dst)"""
+    mindata = np.ascontiguousarray(mindata, np.float64).reshape(-1, 3)
+    tsdata = np.ascontiguousarray(tsdata, np.float64).reshape(-1, 3)
+    m1 = np.ascontiguousarray(m1, np.int64)
+    m2 = np.ascontiguousarray(m2, np.int64)
+    nts = tsdata.shape[0]
+    if m1.size != nts or m2.size != nts:
+        raise ValueError("tsdata, m1 and m2 have different lengths")
+    src, dst, k = np.empty(2 * nts, np.int64), np.empty(2 * nts, np.int64), np.empty(2 * nts, np.float64)
+    n_out, shift = ctypes.c_int64(), ctypes.c_double()
+    st = lib().ngt_pathsample_rates(mindata.shape[0], nts, mindata.ctypes.data_as(_f64p), tsdata.ctypes.data_as(_f64p),
+                                    m1.ctypes.data_as(_i64p), m2.ctypes.data_as(_i64p), float(T), int(device),
+                                    ctypes.byref(n_out), src.ctypes.data_as(_i64p), dst.ctypes.data_as(_i64p),
+                                    k.ctypes.data_as(_f64p), ctypes.byref(shift))
+    if st != NGT_OK:
+        msg = lib().ngt_pathsample_last_error().decode("utf-8", "replace")
+        raise (ValueError if st == NGT_E_INVALID else RuntimeError)(msg)
+    n = n_out.value
+    return src[:n].copy(), dst[:n].copy(), k[:n].copy(), shift.value
 
 
 class Comm(object):

@@ -251,107 +251,6 @@ struct Dissector {
         }
     }
 
-    // Level-synchronous sweep by a team of threads, for the few large subgraphs at the top of the dissection tree whose
-    // two sweeps per split sit on the critical path of the whole analysis (11 + 6 + 3.5 ms of the 38 ms ordering of the
-    // 10^5-minima landscape ran with every other core idle).  A node is claimed for level L+1 by a compare-and-swap on
-    // its level slot; the visiting order is then rebuilt as (level, local id) by a counting sort, so the result does
-    // not depend on the number of threads or on who won a race -- and a single thread runs the very same algorithm.
-    // Whether a subgraph uses this sweep depends on its size only (TEAM_MIN_N).
-    static constexpr int32_t TEAM_MIN_N = 24576;
-    struct SpinBarrier {
-        std::atomic<int> count{0}, gen{0};
-        int n;
-        explicit SpinBarrier(int n_) : n(n_) {}
-        void wait() {
-            const int g = gen.load(std::memory_order_acquire);
-            if (count.fetch_add(1, std::memory_order_acq_rel) == n - 1) {
-                count.store(0, std::memory_order_relaxed);
-                gen.store(g + 1, std::memory_order_release);
-            } else {
-                int spins = 0;
-                while (gen.load(std::memory_order_acquire) == g)
-                    if (++spins > 4000) std::this_thread::yield();
-            }
-        }
-    };
-    static void bfs_team(const Sub &G, int32_t start, std::vector<int32_t> &lvl, std::vector<int32_t> &visit, int32_t &nlev,
-                         int nthreads) {
-        const int T = std::max(1, nthreads);
-        const size_t base = visit.size();
-        std::vector<int32_t> cur;                       // current frontier (any order)
-        cur.reserve(G.n);
-        cur.push_back(start);
-        lvl[start] = 0;
-        std::vector<std::vector<int32_t> > out(T);
-        std::vector<size_t> off(T + 1, 0);
-        const int32_t *adj = G.adj.data(), *ptr = G.ptr.data();
-        int32_t *lv = lvl.data();
-        std::atomic<int> level{0};
-        std::atomic<bool> done{false};
-        SpinBarrier bar(T);
-        auto work = [&](int t) {
-            for (;;) {
-                const int32_t L = level.load(std::memory_order_relaxed);
-                const size_t F = cur.size(), i0 = F * t / T, i1 = F * (t + 1) / T;
-                std::vector<int32_t> &mine = out[t];
-                mine.clear();
-                for (size_t i = i0; i < i1; ++i) {
-                    const int32_t u = cur[i];
-                    for (int32_t e = ptr[u]; e < ptr[u + 1]; ++e) {
-                        const int32_t v = adj[e];
-                        if (__atomic_load_n(lv + v, __ATOMIC_RELAXED) >= 0) continue;
-                        int32_t expect = -1;
-                        if (__atomic_compare_exchange_n(lv + v, &expect, L + 1, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED))
-                            mine.push_back(v);
-                    }
-                }
-                if (T > 1) bar.wait();                  // every claim of this level is made
-                if (t == 0) {
-                    size_t tot = 0;
-                    for (int x = 0; x < T; ++x) { off[x] = tot; tot += out[x].size(); }
-                    off[T] = tot;
-                    cur.resize(tot);
-                    if (tot == 0) done.store(true, std::memory_order_relaxed);
-                    else level.store(L + 1, std::memory_order_relaxed);
-                }
-                if (T > 1) bar.wait();                  // frontier sized, offsets known
-                if (done.load(std::memory_order_relaxed)) return;
-                std::copy(mine.begin(), mine.end(), cur.begin() + off[t]);
-                if (T > 1) bar.wait();                  // next frontier complete
-            }
-        };
-        if (T > 1) {
-            std::vector<std::thread> th;
-            for (int t = 1; t < T; ++t) th.emplace_back(work, t);
-            work(0);
-            for (auto &x : th) x.join();
-        } else {
-            work(0);
-        }
-        nlev = level.load() + 1;
-        // visiting order = (level, local id): counting sort over the nodes this sweep reached
-        std::vector<size_t> cnt(nlev + 1, 0);
-        size_t reached = 0;
-        // (nodes of earlier sweeps of the same call keep their levels too; they were appended to `visit` before and are
-        // told apart by their position: this sweep only runs on a fresh level array or from an unreached start node)
-        std::vector<char> seen;
-        if (base) {
-            seen.assign(G.n, 0);
-            for (size_t i = 0; i < base; ++i) seen[visit[i]] = 1;
-        }
-        for (int32_t v = 0; v < G.n; ++v)
-            if (lv[v] >= 0 && (!base || !seen[v])) { cnt[lv[v] + 1]++; ++reached; }
-        for (int32_t l = 0; l < nlev; ++l) cnt[l + 1] += cnt[l];
-        visit.resize(base + reached);
-        for (int32_t v = 0; v < G.n; ++v)
-            if (lv[v] >= 0 && (!base || !seen[v])) visit[base + cnt[lv[v]]++] = v;
-    }
-    // threads a sweep at recursion depth `depth` may use: the branches of that depth share the machine
-    static int team_threads(int depth) {
-        const unsigned hw = host_threads();
-        return (int)std::max(1u, std::min(8u, hw >> std::min(depth, 4)));
-    }
-
     // induced subgraph on `members` (listed in the order that becomes the new local numbering)
     static void induce(const Sub &G, const std::vector<int32_t> &members, std::vector<int32_t> &newid, Sub &H) {
         H.n = (int32_t)members.size();
@@ -400,8 +299,7 @@ struct Dissector {
         } else {
             lvl.assign(G.n, -1);
             visit.reserve(G.n);
-            if (G.n >= TEAM_MIN_N) bfs_team(G, 0, lvl, visit, nlev, team_threads(depth));
-            else bfs(G, 0, lvl, visit, nlev);
+            bfs(G, 0, lvl, visit, nlev);
         }
         if ((int32_t)visit.size() != G.n) {
             // several components: small ones are packed into leaf-sized bins, large ones dissected on their own
@@ -443,8 +341,7 @@ struct Dissector {
             if (best != 0) {
                 std::fill(lvl.begin(), lvl.end(), -1);
                 visit.clear();
-                if (G.n >= TEAM_MIN_N) bfs_team(G, best, lvl, visit, nlev, team_threads(depth));
-                else bfs(G, best, lvl, visit, nlev);
+                bfs(G, best, lvl, visit, nlev);
             }
         }
         if (nlev < 3) { out.emit_all(G); return; }   // no separator exists (e.g. a clique): one dense supernode

@@ -29,8 +29,11 @@ class RatesFromPathsampleDB(object):
     transition states between the same pair of minima summed, self-connecting transition states dropped.
     """
 
-    def __init__(self, mindata_file, tsdata_file, T):
+    def __init__(self, mindata_file, tsdata_file, T, device=None):
+        """device: CUDA ordinal -> the log rates, the shift and the merge of parallel transition states run on the GPU
+        (`_capi.pathsample_rates`, csrc/pathsample.cu); None -> the vectorised numpy path below (same results)"""
         self.T = T
+        self.device = device
         self.run(mindata_file, tsdata_file)
 
     def _log_equilibrium_occupation_probabilities(self, mindata):
@@ -52,6 +55,17 @@ class RatesFromPathsampleDB(object):
         tsdata = np.atleast_2d(np.genfromtxt(tsdataf, usecols=[0, 1, 2, 3, 4]))
         m1 = tsdata[:, 3].astype(np.int64) - 1
         m2 = tsdata[:, 4].astype(np.int64) - 1
+        nmin = mindata.shape[0]
+        log_Peq = self._log_equilibrium_occupation_probabilities(mindata)
+        self._Peq = np.exp(log_Peq - log_Peq.max())
+        self._nmin = nmin
+        if self.device is not None:
+            from . import _capi
+            self._src, self._dst, self._k, max_log_rate = _capi.pathsample_rates(mindata[:, :3], tsdata[:, :3], m1, m2, self.T,
+                                                                               device=self.device)
+            self.log_rate_subtracted = max_log_rate
+            self.rate_norm = np.exp(-max_log_rate)
+            return
         log_k12 = self.compute_rates(mindata, tsdata, m1)
         log_k21 = self.compute_rates(mindata, tsdata, m2)
         max_log_rate = max(log_k12.max(), log_k21.max())
@@ -65,7 +79,6 @@ class RatesFromPathsampleDB(object):
         src = np.concatenate([m1[keep], m2[keep]])
         dst = np.concatenate([m2[keep], m1[keep]])
         logk = np.concatenate([log_k12[keep], log_k21[keep]])
-        nmin = mindata.shape[0]
         key = src * nmin + dst
         order = np.argsort(key, kind="stable")
         key, logk = key[order], logk[order]
@@ -74,10 +87,6 @@ class RatesFromPathsampleDB(object):
         self._src = (key[starts] // nmin).astype(np.int64)
         self._dst = (key[starts] % nmin).astype(np.int64)
         self._k = np.exp(merged)
-        self._nmin = nmin
-
-        log_Peq = self._log_equilibrium_occupation_probabilities(mindata)
-        self._Peq = np.exp(log_Peq - log_Peq.max())
 
     # ---- the reference's attributes (1-based pathsample ids), built on demand -------------------------------
     @property
@@ -107,10 +116,10 @@ def read_minA(fname):
     return ids
 
 
-def make_rates(directory, T):
+def make_rates(directory, T, device=None):
     """rate constants, equilibrium occupation probabilities and the rate normalisation from a pathsample database
-    (reference utils.py:156-162)"""
-    gen = RatesFromPathsampleDB(os.path.join(directory, "min.data"), os.path.join(directory, "ts.data"), T)
+    (reference utils.py:156-162); device: CUDA ordinal for the on-device path"""
+    gen = RatesFromPathsampleDB(os.path.join(directory, "min.data"), os.path.join(directory, "ts.data"), T, device=device)
     return gen.rate_constants, gen.Peq, gen.rate_norm
 
 

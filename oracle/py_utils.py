@@ -2,9 +2,10 @@
 
 Loop-for-loop Python-3 restatement of the reference's PATHSAMPLE reader (reference kmc_rates/utils.py:13-106,
 Python 2: print statements :74, izip :1, iteritems :66), used to check kmc_rates_b200/utils.py's vectorised version.
-Parity status: pinned only by construction (the reference ships no fixture for this path: no min.data / ts.data in
-the repository and no test of utils.py) -- "parity unpinned" against reference outputs; the restatement follows the
-source line by line.
+Parity status: PINNED.  The reference ships no fixture for this path (no min.data / ts.data in the repository and no
+test of utils.py), so tests/golden/pathsample_golden.json holds outputs of the reference's own utils.py, executed
+through the in-memory Python-2 shim of oracle/make_golden_utils.py; tests/test_utils.py checks this restatement (and
+the product's host and device paths) against them.
 """
 import numpy as np
 

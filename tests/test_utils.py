@@ -90,3 +90,69 @@ def test_pathsample_database_to_rates_on_gpu(tmp_path):
     arr = NGT.from_coo(n, src, dst, k, [a - 1 for a in A], [b - 1 for b in B], weights={i: float(p) for i, p in enumerate(peq)})
     arr.compute_rates()
     assert abs(arr.get_rate_AB() - r[0]) <= 1e-9 * r[0]
+
+
+# ---- pinned against outputs of the reference's own utils.py (tests/golden/pathsample_golden.json, made by
+# ---- oracle/make_golden_utils.py) -----------------------------------------------------------------------------
+def _pathsample_golden():
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "pathsample_golden.json")) as f:
+        return json.load(f)
+
+
+def _write_case(d, case):
+    for name, key in (("min.data", "min_data"), ("ts.data", "ts_data"), ("min.A", "min_A")):
+        with open(os.path.join(d, name), "w") as f:
+            f.write(case[key])
+
+
+def _check_against_golden(case, rates, Peq, norm, rtol):
+    want = {(u, v): float(k) for u, v, k in case["rate_constants"]}
+    assert set(rates) == set(want)
+    for uv, k in want.items():
+        assert abs(rates[uv] - k) <= rtol * k, (case["name"], uv, rates[uv], k)
+    for u, p in case["Peq"]:
+        assert abs(Peq[u] - float(p)) <= 1e-14 * max(float(p), 1e-300)
+    assert abs(norm - float(case["rate_norm"])) <= 1e-14 * float(case["rate_norm"])
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_oracle_restatement_reproduces_the_reference_outputs(tmp_path, idx):
+    from oracle.py_utils import rates_from_pathsample
+    case = _pathsample_golden()["cases"][idx]
+    _write_case(str(tmp_path), case)
+    rates, Peq, norm = rates_from_pathsample(str(tmp_path / "min.data"), str(tmp_path / "ts.data"), case["T"])
+    _check_against_golden(case, rates, Peq, norm, rtol=0.0 if idx < 4 else 1e-15)      # same loop, same order: bit-exact
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_host_ingest_reproduces_the_reference_outputs(tmp_path, idx):
+    from kmc_rates_b200 import utils
+    case = _pathsample_golden()["cases"][idx]
+    _write_case(str(tmp_path), case)
+    rates, Peq, norm = utils.make_rates(str(tmp_path), case["T"])
+    _check_against_golden(case, rates, Peq, norm, rtol=1e-13)      # parallel transition states are summed in another order
+    assert utils.read_minA(str(tmp_path / "min.A")) == case["min_A_ids"]
+
+
+def test_log_sum2_golden():
+    from kmc_rates_b200 import utils
+    for a, b, want in _pathsample_golden()["log_sum2"]:
+        assert utils.log_sum2(float(a), float(b)) == float(want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", range(4))
+def test_device_ingest_reproduces_the_reference_outputs(tmp_path, idx):
+    """csrc/pathsample.cu through the C ABI (ngt_pathsample_rates) against the reference's own outputs"""
+    from kmc_rates_b200 import utils
+    case = _pathsample_golden()["cases"][idx]
+    _write_case(str(tmp_path), case)
+    rates, Peq, norm = utils.make_rates(str(tmp_path), case["T"], device=0)
+    _check_against_golden(case, rates, Peq, norm, rtol=1e-13)
+    host = utils.RatesFromPathsampleDB(str(tmp_path / "min.data"), str(tmp_path / "ts.data"), case["T"])
+    dev = utils.RatesFromPathsampleDB(str(tmp_path / "min.data"), str(tmp_path / "ts.data"), case["T"], device=0)
+    n0, s0, d0, k0, p0 = host.coo()
+    n1, s1, d1, k1, p1 = dev.coo()
+    assert n0 == n1 and np.array_equal(s0, s1) and np.array_equal(d0, d1) and np.allclose(k0, k1, rtol=1e-13, atol=0)
