@@ -1150,11 +1150,17 @@ struct Engine {
         const ngt::Front &F0 = S.fronts[0];
         const int JE = block_end(J), kb = JE - J, fr = F0.f - J;
         const int blk = J / ngt::NB_OUTER;
-        const DFront &P = h_dfronts[2 * blk];
+        // Only the block's own kb rows are factored with the front kernels (a square front); the rows below take the
+        // block's column operations afterwards in one slab launch.  NGT_B200_DIST_RECT_FACTOR=1 (or a cross-check GEMM
+        // path) factors the whole rectangular panel right-looking instead: 8 thin update launches over all rows.
+        static const bool rect = std::getenv("NGT_B200_DIST_RECT_FACTOR") != nullptr;
+        const bool square = !rect && opt.gemm_path == 0;
+        DFront P = h_dfronts[2 * blk];
+        if (square) P.fr = kb;
         double *pan = pan_buf(J) + W_DOUBLES;
         ngt::launch_dist_pack(d_pool.p + F0.off, F0.ld, J, kb, fr, pan, LD_PAN, d_spart.p, d_tauglob.p, stream);
         HostBatch hb;
-        hb.ids = {2 * blk}; hb.f = {P.f}; hb.k = {P.k}; hb.fr = {fr}; hb.max_k = kb; hb.dev_off = 2 * blk;
+        hb.ids = {2 * blk}; hb.f = {P.f}; hb.k = {P.k}; hb.fr = {P.fr}; hb.max_k = kb; hb.dev_off = 2 * blk;
         ngt::LaunchCtx c = ctx(d_pool.p, pool_stride, d_dfronts.p);
         c.f0 = &P;
         wslot_per_step = true;
@@ -1169,6 +1175,7 @@ struct Engine {
         }
         wslot_per_step = false;
         use_lookahead = la;
+        if (square) { ngt::launch_dist_colstrip_slab(pan, LD_PAN, kb, fr, stream); st.n_launches++; }
         CK(cudaMemcpyAsync(pan_buf(J), d_wbuf.p, W_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice, stream));
     }
 
@@ -1199,13 +1206,21 @@ struct Engine {
         c.f0 = &B;
         const int *ids = d_dids.p + 2 * blk + 1;
         double fl = 0;
-        for (int j = J; j < JE; j += ngt::NB_INNER) {
-            c.ko.wslot = (j - J) / ngt::NB_INNER;
-            const int je = std::min(j + ngt::NB_INNER, JE);
-            ngt::launch_rowpanel(c, ids, 1, j, F0.f + 1 - je);
-            const int tb = max_tiles(hb, j, ngt::MODE_B, tm, tn, fl);
-            if (tb > 0) ngt::launch_update(c, ids, 1, j, ngt::MODE_B, tb, 0);
-            st.n_launches += 2;
+        static const bool per_panel = std::getenv("NGT_B200_DIST_PANELWISE_APPLY") != nullptr;   // the 16-launch replay (A/B timing)
+        if (!per_panel && opt.gemm_path == 0) {
+            // all inner panels of the block replayed on the own columns in one launch
+            ngt::launch_dist_apply_slab(d_pool.p + F0.off, F0.ld, F0.f, J, kb, pan, LD_PAN, d_wbuf.p, own(), stream);
+            for (int j = J; j < JE; j += ngt::NB_INNER) (void)max_tiles(hb, j, ngt::MODE_B, tm, tn, fl);   // flop count only
+            st.n_launches += 1;
+        } else {
+            for (int j = J; j < JE; j += ngt::NB_INNER) {
+                c.ko.wslot = (j - J) / ngt::NB_INNER;
+                const int je = std::min(j + ngt::NB_INNER, JE);
+                ngt::launch_rowpanel(c, ids, 1, j, F0.f + 1 - je);
+                const int tb = max_tiles(hb, j, ngt::MODE_B, tm, tn, fl);
+                if (tb > 0) ngt::launch_update(c, ids, 1, j, ngt::MODE_B, tb, 0);
+                st.n_launches += 2;
+            }
         }
         const int jl = J + ((kb - 1) / ngt::NB_INNER) * ngt::NB_INNER;
         const int t1a = max_tiles(hb, jl, ngt::MODE_D1A, tm, tn, fl);

@@ -980,6 +980,18 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// 1-D bulk copies of the copy engine (TMA): global -> shared landing on an mbarrier, shared -> global in a bulk group
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_all() {
+    asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // =====================================================================================================
 // Schur update fed by 2-D tensor-map TMA (`cp.async.bulk.tensor.2d` -> SASS UTMALDG) for large single-front
 // trailing updates.  Per 16-pivot stage the producer warp issues FIVE copies: one 16 x 128 box of A (16 KB) and four
@@ -1736,6 +1748,256 @@ __global__ void dist_root_finish_kernel(double *root, int ld_root, int m, const 
     const int i = idx / (m + 1), jx = idx % (m + 1);
     if (jx < m) root[(long long)i * ld_root + jx] += contrib[i * m + jx];
     else root[(long long)i * ld_root + m] = tau_glob[nI + i];
+}
+
+// Every rank, after the panel broadcast: the block's row operations replayed on the own columns right of the block,
+// all eight inner panels in ONE launch (the per-panel rowpanel + row-strip update launches cost 16 dependent launches
+// per outer block on the critical chain of the multi-GPU loop).  A CTA owns a slab of 64 columns of the block's kb
+// rows in shared memory; inside it a warp owns 8 columns for the whole replay, so the only synchronisation is the
+// staging of the panel's sub-diagonal blocks (the A operands, shared by all warps):
+//   for every inner panel X_j:   S[X_j, :]  = W_j S[X_j, :]                       (U'_j for these columns)
+//                                S[i, :]   += P[i, X_j] S[X_j, :]   rows i below X_j inside the block
+// with W_j from wbuf and P[i, X_j] from the broadcast panel (both FP64 DMMA).
+constexpr int SLAB_W = 64, SLAB_LD = SLAB_W + 4, SLAB_A_LD = NB_INNER + 4;
+size_t dist_apply_slab_smem() { return ((size_t)NB_OUTER * SLAB_LD + (size_t)NB_OUTER * SLAB_A_LD) * sizeof(double); }
+
+__global__ void __launch_bounds__(256, 1)
+dist_apply_slab_kernel(double *M, long long ld, int f, int J, int kb, const double *pan, int ld_pan, const double *W, KOpt ko) {
+    extern __shared__ double smem[];
+    double *S = smem;                              // kb x SLAB_LD: rows J.. of the slab's columns
+    double *As = smem + NB_OUTER * SLAB_LD;        // rows below the current inner panel x its 32 columns
+    const int JE = J + kb;
+    const int c0 = JE + blockIdx.x * SLAB_W;
+    if (c0 >= f) return;
+    // a slab lies inside one 256-column ownership block unless the block is the last, short one: test both ends
+    if (ko.own_G > 1 && !owned_col(ko, c0, f) && !owned_col(ko, min(c0 + SLAB_W, f) - 1, f)) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    // staging goes through cp.async (fire and forget, zero fill for masked slots): a plain load -> store loop stalls on
+    // every element with the 8 warps of this CTA (measured 76 us per launch instead of ~20)
+    // (16-byte copies when the slab starts on an even column and f is even -- always, except for a short last block:
+    // 8-byte LDGSTS instructions were the bottleneck of the first version)
+    if (((c0 | f) & 1) == 0) {
+        const int cc = 2 * (threadIdx.x % (SLAB_W / 2)), c = c0 + cc;
+        const bool col_ok = c < f && owned_col(ko, c, f);          // c even, f even: c + 1 < f and the same owner
+        for (int r = threadIdx.x / (SLAB_W / 2); r < kb; r += 256 / (SLAB_W / 2))
+            cp_async16(S + r * SLAB_LD + cc, col_ok ? M + (long long)(J + r) * ld + c : M, col_ok);
+    } else {
+        const int cc = threadIdx.x % SLAB_W, c = c0 + cc;
+        const bool col_ok = c < f && owned_col(ko, c, f);
+        for (int r = threadIdx.x / SLAB_W; r < kb; r += 256 / SLAB_W)
+            cp_async8(S + r * SLAB_LD + cc, col_ok ? M + (long long)(J + r) * ld + c : M, col_ok);
+    }
+    cp_async_commit();
+    const int wc = warp * 8;                       // this warp's 8 columns of the slab
+    for (int j = 0; j < kb; j += NB_INNER) {
+        const int nbp = min(NB_INNER, kb - j), je = j + nbp;
+        const int nbelow = kb - je;
+        __syncthreads();                           // previous panel's A block no longer needed
+        if ((nbp & 1) == 0) {
+            const int q = 2 * (threadIdx.x % (NB_INNER / 2));
+            for (int r = threadIdx.x / (NB_INNER / 2); r < nbelow; r += 256 / (NB_INNER / 2))
+                cp_async16(As + r * SLAB_A_LD + q, q < nbp ? pan + (long long)(je + r) * ld_pan + j + q : pan, q < nbp);
+        } else {
+            const int q = threadIdx.x % NB_INNER;
+            for (int r = threadIdx.x / NB_INNER; r < nbelow; r += 256 / NB_INNER)
+                cp_async8(As + r * SLAB_A_LD + q, q < nbp ? pan + (long long)(je + r) * ld_pan + j + q : pan, q < nbp);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();                        // (also the slab itself, on the first panel)
+        __syncthreads();
+        // U'_j = W_j S[X_j, own columns]
+        const double *Wj = W + (long long)(j / NB_INNER) * NB_INNER * NB_INNER;
+        double bf[NB_INNER / 4];
+#pragma unroll
+        for (int k4 = 0; k4 < NB_INNER / 4; ++k4) {
+            const int kk = k4 * 4 + t4;
+            bf[k4] = kk < nbp ? S[(j + kk) * SLAB_LD + wc + g] : 0.0;
+        }
+        double u[4][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            u[mi][0] = u[mi][1] = 0.0;
+#pragma unroll
+            for (int k4 = 0; k4 < NB_INNER / 4; ++k4) dmma884(u[mi][0], u[mi][1], __ldg(Wj + (mi * 8 + g) * NB_INNER + k4 * 4 + t4), bf[k4]);
+        }
+        __syncwarp();                              // every lane has read the old rows of this warp's columns
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const int r = mi * 8 + g;
+            if (r < nbp) { S[(j + r) * SLAB_LD + wc + 2 * t4] = u[mi][0]; S[(j + r) * SLAB_LD + wc + 2 * t4 + 1] = u[mi][1]; }
+        }
+        __syncwarp();
+        // rows below X_j inside the block: S[i, :] += P[i, X_j] U'_j
+#pragma unroll
+        for (int k4 = 0; k4 < NB_INNER / 4; ++k4) {
+            const int kk = k4 * 4 + t4;
+            bf[k4] = kk < nbp ? S[(j + kk) * SLAB_LD + wc + g] : 0.0;
+        }
+        // four row tiles at a time: four independent accumulator chains (a single chain of 8 dependent DMMAs per tile
+        // left the tensor pipe idle most of the time)
+        for (int r0 = 0; r0 < nbelow; r0 += 32) {
+            double cv[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u * 8 + g;      // row below the panel (As index); rows >= nbelow: masked
+                const double *srow = S + (je + r) * SLAB_LD + wc + 2 * t4;
+                cv[u][0] = r < nbelow ? srow[0] : 0.0;
+                cv[u][1] = r < nbelow ? srow[1] : 0.0;
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < NB_INNER / 4; ++k4)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = r0 + u * 8 + g;
+                    dmma884(cv[u][0], cv[u][1], r < nbelow ? As[r * SLAB_A_LD + k4 * 4 + t4] : 0.0, bf[k4]);
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u * 8 + g;
+                if (r < nbelow) {
+                    double *srow = S + (je + r) * SLAB_LD + wc + 2 * t4;
+                    srow[0] = cv[u][0];
+                    srow[1] = cv[u][1];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int cc = threadIdx.x % SLAB_W, c = c0 + cc;
+        if (c < f && owned_col(ko, c, f))
+            for (int r = threadIdx.x / SLAB_W; r < kb; r += 256 / SLAB_W) M[(long long)(J + r) * ld + c] = S[r * SLAB_LD + cc];
+    }
+}
+
+void launch_dist_apply_slab(double *M, long long ld, int f, int J, int kb, const double *pan, int ld_pan, const double *W,
+                            KOpt ko, cudaStream_t s) {
+    const int ncols = f - (J + kb);
+    if (ncols <= 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(dist_apply_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dist_apply_slab_smem());
+        attr_set = true;
+    }
+    dist_apply_slab_kernel<<<(ncols + SLAB_W - 1) / SLAB_W, 256, dist_apply_slab_smem(), s>>>(M, ld, f, J, kb, pan, ld_pan, W, ko);
+}
+
+// Owner, after the SQUARE factorisation of the block (its kb rows only): the rows below the block, restricted to the
+// block's columns and the tau column, take the block's column operations in ONE launch -- the right-looking
+// factorisation of the full rectangular panel spent 8 thin (K = 32) update launches over up to 16 384 rows on this.
+// A CTA owns 64 rows of the panel in shared memory, a warp 8 of them for the whole replay:
+//   for every inner panel X_j:  P[i, X_j] is final (the multiplier that travels with the panel);
+//                               P[i, c] += P[i, X_j] U'_j[X_j, c]   for the block columns c right of X_j and for tau
+// U'_j comes from the factored block rows of the same panel buffer (staged per inner panel, shared by the warps).
+constexpr int CS_ROWS = 64;
+size_t dist_colstrip_smem(int ld_pan) { return (size_t)(CS_ROWS + NB_INNER) * ld_pan * sizeof(double); }
+
+// Shared-memory tiles keep the panel's own row stride (ld_pan), so that a tile is ONE contiguous piece of the panel
+// buffer and is staged by ONE bulk copy of the copy engine (cp.async.bulk onto an mbarrier; written back the same
+// way).  Measured on the way here: element-wise cp.async staging cost 40 % of the kernel in LDGSTS issue alone, one bulk
+// copy per row ~60 cycles each in the copy engine (32 rows x 8 panels), one copy per tile is free.  The stride
+// (264 = 8 mod 16 doubles) makes the fragment loads 2-way bank conflicted; the kernel is bound by the DMMA pipe.
+__global__ void __launch_bounds__(256, 1)
+dist_colstrip_slab_kernel(double *pan, int ld_pan, int kb, int fr) {
+    extern __shared__ __align__(16) double smem[];
+    const int LD = ld_pan, ncol = kb + 2;                // block columns, the S column (carried, unused), tau
+    double *S = smem;                                    // CS_ROWS x LD
+    double *Bs = smem + CS_ROWS * LD;                    // NB_INNER x LD: rows X_j of the factored block (U'_j right of X_j)
+    const int r0 = kb + blockIdx.x * CS_ROWS;
+    if (r0 >= fr) return;
+    const int nrows = min(CS_ROWS, fr - r0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    __shared__ unsigned long long bar;
+    unsigned phase = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = nrows * LD + threadIdx.x; i < CS_ROWS * LD; i += 256) S[i] = 0.0;      // rows past the panel's end
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned bytes = (unsigned)((size_t)nrows * LD * sizeof(double));
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(S, pan + (long long)r0 * ld_pan, bytes, &bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    double *srow = S + (warp * 8 + g) * LD;              // this lane's row of the warp's 8-row tile
+#ifdef NGT_DN_CLOCKS
+    long long dn_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dn_last = clock64();
+#endif
+    for (int j = 0; j < kb; j += NB_INNER) {
+        const int nbp = min(NB_INNER, kb - j), je = j + nbp;
+        __syncthreads();                                 // every warp is done reading the previous U'_j
+        DN_T(0);
+        // (no proxy fence: the copy overwrites what the warps only READ in the previous step, and the block barrier above
+        // orders those reads before this issue)
+        if (threadIdx.x == 0) {
+            const unsigned bytes = (unsigned)((size_t)nbp * LD * sizeof(double));
+            mbar_expect_tx(&bar, bytes);
+            bulk_g2s(Bs, pan + (long long)j * ld_pan, bytes, &bar);
+        }
+        DN_T(1);
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        DN_T(2);
+        double a[NB_INNER / 4];
+#pragma unroll
+        for (int k4 = 0; k4 < NB_INNER / 4; ++k4) {
+            const int kk = k4 * 4 + t4;
+            a[k4] = kk < nbp ? srow[j + kk] : 0.0;       // (rows of Bs past nbp are stale: their multipliers are zero)
+        }
+        for (int ct0 = je / 8; ct0 * 8 < ncol; ct0 += 4) {      // four column tiles = four independent accumulator chains
+            double cv[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = (ct0 + u) * 8 + 2 * t4;
+                const bool ok = (ct0 + u) * 8 < ncol;
+                cv[u][0] = ok ? srow[c] : 0.0;
+                cv[u][1] = ok ? srow[c + 1] : 0.0;
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < NB_INNER / 4; ++k4)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int cb = (ct0 + u) * 8 + g;    // columns left of je (only in a short last panel) must not contribute
+                    const bool ok = (ct0 + u) * 8 < ncol && cb >= je && k4 * 4 + t4 < nbp;
+                    dmma884(cv[u][0], cv[u][1], a[k4], ok ? Bs[(k4 * 4 + t4) * LD + cb] : 0.0);
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if ((ct0 + u) * 8 < ncol) {
+                    const int c = (ct0 + u) * 8 + 2 * t4;
+                    srow[c] = cv[u][0];
+                    srow[c + 1] = cv[u][1];
+                }
+        }
+        __syncwarp();                                    // the tile's columns X_{j+1} are read by other lanes next
+        DN_T(3);
+    }
+    fence_proxy_async_smem();                            // the rows go back through the copy engine (generic writes -> async reads)
+    __syncthreads();
+    DN_T(4);
+    if (threadIdx.x == 0) {
+        bulk_s2g(pan + (long long)r0 * ld_pan, S, (unsigned)((size_t)nrows * LD * sizeof(double)));
+        bulk_commit_wait_all();
+    }
+    DN_T(5);
+#ifdef NGT_DN_CLOCKS
+    if (threadIdx.x == 0 && blockIdx.x == 0 && kb == NB_OUTER)
+        printf("colstrip slab clocks (CTA 0, %d CTAs): barrier %lld  issue staging %lld  wait staging %lld  dmma %lld  final barrier %lld  write back %lld\n",
+               (int)gridDim.x, dn_acc[0], dn_acc[1], dn_acc[2], dn_acc[3], dn_acc[4], dn_acc[5]);
+#endif
+}
+
+void launch_dist_colstrip_slab(double *pan, int ld_pan, int kb, int fr, cudaStream_t s) {
+    if (fr <= kb) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(dist_colstrip_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dist_colstrip_smem(ld_pan));
+        attr_set = true;
+    }
+    dist_colstrip_slab_kernel<<<(fr - kb + CS_ROWS - 1) / CS_ROWS, 256, dist_colstrip_smem(ld_pan), s>>>(pan, ld_pan, kb, fr);
 }
 
 void launch_dist_rowsum(const double *M, int ld, int f, int J, int JE, KOpt ko, double *out, cudaStream_t s) {

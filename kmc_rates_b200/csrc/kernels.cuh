@@ -194,6 +194,13 @@ void launch_phase2_collect(const LaunchCtx &c, const double *p2pool, long long p
 
 // ---- multi-GPU dense path helpers (see kernels.cu) --------------------------------------------------------
 void launch_dist_rowsum(const double *M, int ld, int f, int J, int JE, KOpt ko, double *out, cudaStream_t s);
+// owner: the block's column operations on the panel rows below the block (block columns + tau), one launch; the block
+// rows of `pan` must hold the factored square block (see kernels.cu)
+void launch_dist_colstrip_slab(double *pan, int ld_pan, int kb, int fr, cudaStream_t s);
+// the block's row operations (all inner panels) on the own columns right of the block, one launch (see kernels.cu):
+// M = the big matrix, pan = the broadcast panel (rows J.., ld_pan), W = the block's inner-panel inverses (wbuf slots)
+void launch_dist_apply_slab(double *M, long long ld, int f, int J, int kb, const double *pan, int ld_pan, const double *W,
+                            KOpt ko, cudaStream_t s);
 void launch_dist_pack(const double *M, int ld, int J, int kb, int fr, double *pan, int ld_pan, const double *S,
                       const double *tau_glob, cudaStream_t s);
 void launch_dist_tau(const double *pan, int ld_pan, int kb, int fr, int J, double *tau_glob, cudaStream_t s);

@@ -1,0 +1,7 @@
+set -x
+cd $GRAFT_REPO_ROOT
+O=gpurun_out/r2k; mkdir -p $O
+timeout 600 python -m pytest tests/test_distributed.py -m gpu -q > $O/pytest.log 2>&1; tail -3 $O/pytest.log
+timeout 300 python scripts/profile_step.py dist 16384 > $O/dist_new.log 2>&1; tail -n 1 $O/dist_new.log
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/launches_dist.csv python scripts/profile_step.py dist 8192 --warmup 0 > $O/ncu_dist.log 2>&1
+echo done

@@ -31,6 +31,18 @@ elif a.workload == "c5":
     import bench
     K = bench.c5_rate_matrices(torch, 0, a.nbatch or bench.C5_NB)
     h = Handle.from_dense(K, [0], [bench.C5_N - 1], gemm_path=a.gemm)
+elif a.workload == "dist":
+    # the multi-GPU dense path with a world of one rank (same launches per block as every rank runs at N > 1)
+    from kmc_rates_b200 import _capi
+    N = a.size or 8192
+    K = torch.rand(N, N, dtype=torch.float64, device="cuda"); K.fill_diagonal_(0)
+    h = Handle.from_dense(K, [0], [1], gemm_path=a.gemm)
+    comm = _capi.Comm(0, 0, 1, lambda b: b)
+    for _ in range(a.warmup):
+        h.dist_phase_one(comm)
+    ms = h.dist_phase_one(comm)
+    print("workload dist n=%d: %.3f ms" % (N, ms))
+    sys.exit(0)
 elif a.workload == "dense":
     N = a.size or 8192
     K = torch.rand(N, N, dtype=torch.float64, device="cuda"); K.fill_diagonal_(0)
