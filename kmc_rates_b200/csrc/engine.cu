@@ -373,6 +373,7 @@ struct Engine {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         for (auto &e : sync_ev)
             if (e) cudaEventDestroy(e);
+        if (bulk_gate) cudaEventDestroy(bulk_gate);
         if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -410,6 +411,7 @@ struct Engine {
         CK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
         CK(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, prio_lo));
         for (auto &x : sync_ev) CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&bulk_gate, cudaEventDisableTiming));
         for (auto &x : ev) CK(cudaEventCreate(&x));
         d_err.alloc(1);
         CK(cudaMemset(d_err.p, 0, sizeof(int)));
@@ -1166,15 +1168,21 @@ struct Engine {
         wslot_per_step = true;
         const bool la = use_lookahead;
         use_lookahead = false;
+        // the panel buffer is disjoint from the region a pending bulk update (D2 of the previous block, second stream)
+        // writes: eliminate_chunk must not make the main stream wait for it after the factorisation
+        const bool pend = d2_pending;
+        d2_pending = false;
         try {
             eliminate_chunk(c, hb, d_dids.p);
         } catch (...) {
             wslot_per_step = false;
             use_lookahead = la;
+            d2_pending = pend;
             throw;
         }
         wslot_per_step = false;
         use_lookahead = la;
+        d2_pending = pend;
         if (square) { ngt::launch_dist_colstrip_slab(pan, LD_PAN, kb, fr, stream); st.n_launches++; }
         CK(cudaMemcpyAsync(pan_buf(J), d_wbuf.p, W_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice, stream));
     }
@@ -1190,7 +1198,9 @@ struct Engine {
     // Look-ahead: only the strips the NEXT block needs (its columns, its rows) are updated on the main stream; the
     // rest of the trailing update runs on the second stream and overlaps the next block's row sums, all-reduce,
     // panel factorisation and broadcast.
-    void dist_apply_enqueue(int J) {
+    // defer_bulk: do not launch the bulk of the trailing update (D2) yet -- dist_bulk_enqueue(J) does it later (the rank
+    // that factors the NEXT block holds its own bulk update back until that factorisation is in the queue)
+    void dist_apply_enqueue(int J, bool defer_bulk = false) {
         const ngt::Front &F0 = S.fronts[0];
         const int JE = block_end(J), kb = JE - J, fr = F0.f - J;
         const int blk = J / ngt::NB_OUTER;
@@ -1229,22 +1239,47 @@ struct Engine {
         // the strips (and everything after them) touch the region the previous block's D2 was writing
         if (d2_pending) { CK(cudaStreamWaitEvent(stream, sync_event(1), 0)); d2_pending = false; }
         if (t1a + t1b > 0) { ngt::launch_update(c, ids, 1, jl, ngt::MODE_D1, t1a + t1b, t1a); st.n_launches++; }
+        st.schur_flops += fl / dist_G;   // region flops; a rank performs its 1/G share of the columns
+        bulk_J = -1;
         if (t2 > 0) {
             if (use_lookahead) {
-                CK(cudaEventRecord(sync_event(0), stream));
-                CK(cudaStreamWaitEvent(stream2, sync_event(0), 0));
-                ngt::LaunchCtx c2 = c;
-                c2.stream = stream2;
-                ngt::launch_update(c2, ids, 1, jl, ngt::MODE_D2, t2, 0);
-                CK(cudaEventRecord(sync_event(1), stream2));
-                d2_pending = true;
+                CK(cudaEventRecord(sync_event(0), stream));     // "the strips of block J are updated"
+                bulk_J = J;
+                bulk_tiles = t2;
+                if (!defer_bulk) dist_bulk_enqueue();
             } else {
                 ngt::launch_update(c, ids, 1, jl, ngt::MODE_D2, t2, 0);
+                st.n_launches++;
             }
-            st.n_launches++;
         }
-        st.schur_flops += fl / dist_G;   // region flops; a rank performs its 1/G share of the columns
     }
+
+    // the bulk (D2) of block bulk_J's trailing update, on the second stream; after_main: it must also wait for what the
+    // main stream holds at this moment (the owner of the next block: its panel factorisation -- both would otherwise
+    // fight for the same SMs and the factorisation, which every other rank waits for, would lose)
+    int bulk_J = -1, bulk_tiles = 0;
+    void dist_bulk_enqueue(bool after_main = false) {
+        if (bulk_J < 0) return;
+        const int J = bulk_J, blk = J / ngt::NB_OUTER;
+        const int JE = block_end(J), kb = JE - J;
+        const int jl = J + ((kb - 1) / ngt::NB_INNER) * ngt::NB_INNER;
+        const DFront &B = h_dfronts[2 * blk + 1];
+        ngt::LaunchCtx c2 = ctx(d_pool.p, pool_stride, d_dfronts.p);
+        c2.ko = own();
+        c2.f0 = &B;
+        c2.stream = stream2;
+        CK(cudaStreamWaitEvent(stream2, sync_event(0), 0));
+        if (after_main) {
+            CK(cudaEventRecord(bulk_gate, stream));
+            CK(cudaStreamWaitEvent(stream2, bulk_gate, 0));
+        }
+        ngt::launch_update(c2, d_dids.p + 2 * blk + 1, 1, jl, ngt::MODE_D2, bulk_tiles, 0);
+        CK(cudaEventRecord(sync_event(1), stream2));
+        d2_pending = true;
+        st.n_launches++;
+        bulk_J = -1;
+    }
+    cudaEvent_t bulk_gate = nullptr;
 
     void dist_root_contrib_enqueue() {
         const ngt::Front &F0 = S.fronts[0];
@@ -1304,12 +1339,16 @@ struct Engine {
             NK(nc.AllReduce(d_spart.p, d_spart.p, (size_t)block, NcclApi::F64, NcclApi::SUM, cm.comm, stream));
             const int owner = (J / block) % cm.world;
             if (cm.rank == owner) dist_factor_enqueue(J);
+            dist_bulk_enqueue(true);      // the previous block's bulk update, if this rank held it back (see below)
             double *p = nullptr;
             int64_t cnt = 0;
             dist_panel(J, &p, &cnt);
             NK(nc.Broadcast(p, p, (size_t)cnt, NcclApi::F64, owner, cm.comm, stream));
-            dist_apply_enqueue(J);
+            // the rank that factors the next block keeps its bulk update out of that factorisation's way
+            const bool next_owner = cm.world > 1 && J + block < (int)S.nI && cm.rank == ((J / block) + 1) % cm.world;
+            dist_apply_enqueue(J, next_owner);
         }
+        dist_bulk_enqueue();
         dist_root_contrib_enqueue();
         NK(nc.AllReduce(d_rootc.p, d_rootc.p, (size_t)m * m, NcclApi::F64, NcclApi::SUM, cm.comm, stream));
         CK(cudaEventRecord(ev[2], stream));
