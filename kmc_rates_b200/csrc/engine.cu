@@ -295,7 +295,7 @@ struct Engine {
     // 2-D tensor maps over the single front of a dense handle (A box 16 x 128, B box 16 x 16, 128-byte swizzle)
     CUtensorMap tmapA{}, tmapB{};
     bool have_tmaps = false;
-    bool use_tmap = std::getenv("NGT_B200_NO_TMAP") == nullptr;
+    bool use_tmap = true;     // tensor-map (TMA) fed kernel for the large trailing updates of a dense handle
     void make_tensor_maps() {
         have_tmaps = false;
         if (!dense || nbatch != 1 || S.nI <= 0) return;
@@ -703,26 +703,10 @@ struct Engine {
         return mx;
     }
 
-    // Optional: process the networks of a batched handle in chunks whose fronts fit in L2 together, so a chunk's
-    // matrices stay cache resident across its panel steps instead of streaming through HBM once per step.
-    void eliminate(const ngt::LaunchCtx &c0, const HostBatch &b, const int *dev_ids) {
-        double bytes_per_net = 0;
-        for (size_t i = 0; i < b.ids.size(); ++i) bytes_per_net += 8.0 * b.f[i] * (b.f[i] + 8.0);
-        int chunk = c0.nbatch;
-        // measured on config 5 (4096 x 256 nodes): chunks of 148 networks ran slower (14.1 vs 12.1 ms) because each
-        // launch then holds a single wave of latency-bound CTAs; off unless NGT_B200_L2_CHUNK_MB is set
-        static const char *chunk_env = std::getenv("NGT_B200_L2_CHUNK_MB");
-        if (chunk_env && c0.nbatch > 1 && b.max_k > ngt::NB_INNER)
-            chunk = (int)std::max(1.0, std::min((double)c0.nbatch, std::atof(chunk_env) * 1e6 / std::max(1.0, bytes_per_net)));
-        for (int net0 = 0; net0 < c0.nbatch; net0 += chunk) {
-            ngt::LaunchCtx c = c0;
-            c.nbatch = std::min(chunk, c0.nbatch - net0);
-            c.pool = c0.pool + (long long)net0 * c0.pool_stride;
-            c.wbuf = c0.wbuf + (long long)net0 * c0.maxfb * ngt::NB_INNER * ngt::NB_INNER;
-            c.rsbuf = c0.rsbuf + (long long)net0 * c0.maxfb * c0.maxchunks * ngt::NB_INNER;
-            eliminate_chunk(c, b, dev_ids);
-        }
-    }
+    // (Processing the networks of a batched handle in L2-sized chunks was measured slower on config 5 -- 14.1 vs 12.1 ms,
+    // each launch then holds a single wave of latency-bound CTAs -- and is gone; batches of small complete networks now
+    // take the whole-network kernel instead.)
+    void eliminate(const ngt::LaunchCtx &c0, const HostBatch &b, const int *dev_ids) { eliminate_chunk(c0, b, dev_ids); }
 
     void eliminate_chunk(const ngt::LaunchCtx &c, const HostBatch &b, const int *dev_ids) {
         const int nbatch = c.nbatch;   // shadows the member: flops and look-ahead sizing are per chunk
@@ -1153,10 +1137,9 @@ struct Engine {
         const int JE = block_end(J), kb = JE - J, fr = F0.f - J;
         const int blk = J / ngt::NB_OUTER;
         // Only the block's own kb rows are factored with the front kernels (a square front); the rows below take the
-        // block's column operations afterwards in one slab launch.  NGT_B200_DIST_RECT_FACTOR=1 (or a cross-check GEMM
-        // path) factors the whole rectangular panel right-looking instead: 8 thin update launches over all rows.
-        static const bool rect = std::getenv("NGT_B200_DIST_RECT_FACTOR") != nullptr;
-        const bool square = !rect && opt.gemm_path == 0;
+        // block's column operations afterwards in one slab launch.  (The cross-check GEMM paths factor the whole
+        // rectangular panel right-looking instead: 8 thin update launches over all rows, the round-1 schedule.)
+        const bool square = opt.gemm_path == 0;
         DFront P = h_dfronts[2 * blk];
         if (square) P.fr = kb;
         double *pan = pan_buf(J) + W_DOUBLES;
@@ -1216,8 +1199,7 @@ struct Engine {
         c.f0 = &B;
         const int *ids = d_dids.p + 2 * blk + 1;
         double fl = 0;
-        static const bool per_panel = std::getenv("NGT_B200_DIST_PANELWISE_APPLY") != nullptr;   // the 16-launch replay (A/B timing)
-        if (!per_panel && opt.gemm_path == 0) {
+        if (opt.gemm_path == 0) {
             // all inner panels of the block replayed on the own columns in one launch
             ngt::launch_dist_apply_slab(d_pool.p + F0.off, F0.ld, F0.f, J, kb, pan, LD_PAN, d_wbuf.p, own(), stream);
             for (int j = J; j < JE; j += ngt::NB_INNER) (void)max_tiles(hb, j, ngt::MODE_B, tm, tn, fl);   // flop count only
@@ -1334,19 +1316,36 @@ struct Engine {
         CK(cudaEventRecord(ev[0], stream));     // the timed region includes the ingest kernel, like a single-GPU step
         dist_begin(cm.rank, cm.world);
         const int block = ngt::NB_OUTER;
+        // NGT_B200_DIST_TRACE=1: CUDA events between the stages of every block on the main stream; the per-stage sums
+        // are printed to stderr afterwards (where does a block's time go at this world size?)
+        static const bool trace = std::getenv("NGT_B200_DIST_TRACE") != nullptr;
+        std::vector<cudaEvent_t> tev;
+        auto mark = [&] {
+            if (!trace) return;
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            CK(cudaEventRecord(e, stream));
+            tev.push_back(e);
+        };
         for (int J = 0; J < (int)S.nI; J += block) {
+            mark();
             dist_rowsum_enqueue(J);
+            mark();
             NK(nc.AllReduce(d_spart.p, d_spart.p, (size_t)block, NcclApi::F64, NcclApi::SUM, cm.comm, stream));
+            mark();
             const int owner = (J / block) % cm.world;
             if (cm.rank == owner) dist_factor_enqueue(J);
             dist_bulk_enqueue(true);      // the previous block's bulk update, if this rank held it back (see below)
+            mark();
             double *p = nullptr;
             int64_t cnt = 0;
             dist_panel(J, &p, &cnt);
             NK(nc.Broadcast(p, p, (size_t)cnt, NcclApi::F64, owner, cm.comm, stream));
+            mark();
             // the rank that factors the next block keeps its bulk update out of that factorisation's way
             const bool next_owner = cm.world > 1 && J + block < (int)S.nI && cm.rank == ((J / block) + 1) % cm.world;
             dist_apply_enqueue(J, next_owner);
+            mark();
         }
         dist_bulk_enqueue();
         dist_root_contrib_enqueue();
@@ -1358,6 +1357,21 @@ struct Engine {
             float t = 0;
             CK(cudaEventElapsedTime(&t, ev[0], ev[2]));
             *ms = t;
+        }
+        if (trace) {
+            const char *names[5] = {"row sums", "all-reduce (incl. waiting for the slowest rank)", "panel factorisation (owner only)",
+                                    "panel broadcast (incl. waiting for the owner)", "row operations + strips (incl. waiting for the bulk update)"};
+            double sum[5] = {0, 0, 0, 0, 0};
+            for (size_t i = 0; i + 5 < tev.size() + 1 && i + 5 <= tev.size() - 1 + 1; i += 6)
+                for (int k = 0; k < 5 && i + k + 1 < tev.size(); ++k) {
+                    float t = 0;
+                    cudaEventElapsedTime(&t, tev[i + k], tev[i + k + 1]);
+                    sum[k] += t;
+                }
+            std::fprintf(stderr, "[ngt dist trace] rank %d of %d, %d blocks:", cm.rank, cm.world, (int)(tev.size() / 6));
+            for (int k = 0; k < 5; ++k) std::fprintf(stderr, "  %s %.2f ms;", names[k], sum[k]);
+            std::fprintf(stderr, "\n");
+            for (auto &e : tev) cudaEventDestroy(e);
         }
     }
 

@@ -177,43 +177,13 @@ void launch_rowsum(const LaunchCtx &c, const int *ids, int nfb, int j, int max_c
 //   s_u  = sum_{v >= je} P[j+u, v]                (mass leaving the panel; GTH row sums)     -- all warps
 //   W    = (I - P_XX)^-1 by subtraction-free Gauss-Jordan; pivot d_p = sum_{q > p} T[p,q] + s_p  -- 4 warps
 //   U'   = W [P_XR | tau_X] for fronts with few columns                                        -- all warps
-// Gauss-Jordan layout: 4 warps x 32 lanes, lane u = row u, warp w = columns 8w..8w+7, in place in registers: at
-// step p columns < p hold the accumulated inverse G, columns > p the remaining T.  T[u][u] is never used: the
-// self-loop mass is discarded and every pivot is re-summed from off-diagonal entries only, which keeps the
-// recurrence free of subtractions.
-// The 32-step dependency chain is kept short by computing the NEXT pivot one step ahead:
-//     d_{p+1} = A + f B,   A = sum_{q>p+1} T[p+1][q] + s_{p+1},  B = sum_{q>p+1} T[p][q] + s_p,  f = T[p+1][p] / d_p
-// (the same non-negative terms, grouped so that A and B are known before 1/d_p is).  Every thread evaluates this
-// scalar recurrence redundantly, so the chain reciprocal -> multiply -> fma -> reciprocal never leaves the
-// register file; rows, columns and partial sums are handed over through double-buffered shared memory with one
-// named barrier per step, off the chain.
+// The Gauss-Jordan is blocked (gj_blocked below): 8-pivot diagonal blocks inverted by one warp with the scalar GTH
+// recurrence, everything else as 8 x 8 x 8 DMMA products.  T[u][u] is never used: the self-loop mass is discarded and
+// every pivot is re-summed from off-diagonal entries only, which keeps the recurrence free of subtractions.
 // NT = 512: single-front launches at the top of the assembly tree (16 warps share the row sums and the row panel);
 // NT = 128: launches with many fronts (leaf levels, batched networks, phase-2 tasks), 4 CTAs per SM.
 // =====================================================================================================
-constexpr int GJ_WARPS = 4, GJ_COLS = NB_INNER / GJ_WARPS;
-
-// X[i] with a warp-uniform runtime i, without demoting the register array to local memory
-__device__ __forceinline__ double gj_get(const double (&X)[GJ_COLS], int i) {
-    double v = X[0];
-    switch (i) {
-        case 1: v = X[1]; break; case 2: v = X[2]; break; case 3: v = X[3]; break; case 4: v = X[4]; break;
-        case 5: v = X[5]; break; case 6: v = X[6]; break; case 7: v = X[7]; break; default: break;
-    }
-    return v;
-}
-__device__ __forceinline__ void gj_set(double (&X)[GJ_COLS], int i, double v) {
-    switch (i) {
-        case 0: X[0] = v; break; case 1: X[1] = v; break; case 2: X[2] = v; break; case 3: X[3] = v; break;
-        case 4: X[4] = v; break; case 5: X[5] = v; break; case 6: X[6] = v; break; default: X[7] = v; break;
-    }
-}
-// sum of the local columns i >= t (t warp-uniform), fixed summation tree
-__device__ __forceinline__ double gj_tail_sum(const double (&X)[GJ_COLS], int t) {
-    double m[GJ_COLS];
-#pragma unroll
-    for (int i = 0; i < GJ_COLS; ++i) m[i] = (i >= t) ? X[i] : 0.0;
-    return ((m[0] + m[1]) + (m[2] + m[3])) + ((m[4] + m[5]) + (m[6] + m[7]));
-}
+constexpr int GJ_WARPS = 4;
 __device__ __forceinline__ void gj_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(GJ_WARPS * 32) : "memory"); }
 
 #ifdef NGT_PANEL_CLOCKS
@@ -237,9 +207,10 @@ __device__ long long g_gj_clk[8];
 //         column rides as a fifth tile), and the block's own columns become G[r][B] W_b: they join the inverse.
 //   After the four block steps columns 0..31 of G hold W.  Every quantity is a sum of products of non-negative
 //   numbers, as in the scalar recurrence (Wales' 1-P_xx as a sum of off-diagonal probabilities, blocked).
-//   The scalar 32-step recurrence (kept below under NGT_OLD_GJ) issued ~37 warp-wide FP64 instructions per pivot at
-//   8 cycles each on all four schedulers (690 cycles per pivot measured); here the scalar chain runs over 8 columns in
-//   one warp and the O(32^2) work per pivot moves to ~40 DMMAs per block.
+//   The scalar 32-step recurrence of round 1 (4 warps, lane = row, one named barrier per pivot) issued ~37 warp-wide
+//   FP64 instructions per pivot at 8 cycles each on all four schedulers: 23.6k cycles per panel measured.  Here the
+//   scalar chain runs over 8 columns in one warp and the O(32^2) work per pivot moves to ~40 DMMAs per block: 12.2k
+//   cycles for the four inversions + 2.8k for the DMMA steps (csrc/tools/panel_bench.cu, -DNGT_PANEL_CLOCKS).
 // -----------------------------------------------------------------------------------------------------
 constexpr int GJ_LD = NB_INNER + 4;      // = 4 mod 16 doubles: conflict-free DMMA fragment loads; column NB_INNER = s
 constexpr int WB_LD = 12;                // row stride of the 8 x 8 inverse W_b
@@ -425,15 +396,7 @@ panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const in
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     __shared__ double Xs[NB_INNER][GJ_LD];          // T (and s in column NB_INNER) on the way in, W on the way out
-#ifdef NGT_OLD_GJ
-    __shared__ double Ss[NB_INNER];
-    // Gauss-Jordan hand-over, double buffered by step parity: pivot row, pivot column, s of every row and the
-    // per-warp partial sums of every row over the columns two past the pivot
-    __shared__ __align__(16) double Row[2][NB_INNER], Col[2][NB_INNER], Sv[2][NB_INNER], Ps[2][GJ_WARPS][NB_INNER];
-    __shared__ double D0;
-#else
     __shared__ double Wb8[8 * WB_LD];
-#endif
     __shared__ double xs[NB_INNER * (CW + 4)];
     __shared__ double Wd[NB_INNER * WD_LD];
     NGT_CLK(0);
@@ -501,99 +464,14 @@ panel_kernel(double *pool, long long pool_stride, const DFront *fronts, const in
             const double sum = (u < nbp) ? rowsum[i] : 1.0;   // padding rows behave like isolated absorbing nodes
             const double t = (u < nbp && lane < nbp && lane != u) ? M[(long long)(j + u) * F.ld + j + lane] : 0.0;
             Xs[u][lane] = t;
-#ifdef NGT_OLD_GJ
-            if (lane == 0) Ss[u] = sum;
-            if (u == 0) {                       // first pivot, summed directly
-                const double d0 = warp_sum(t) + sum;
-                if (lane == 0) D0 = d0;
-            }
-#else
             if (lane < GJ_LD - NB_INNER) Xs[u][NB_INNER + lane] = (lane == 0) ? sum : 0.0;
-#endif
         }
     }
     __syncthreads();
     NGT_CLK(1);
 
-#ifndef NGT_OLD_GJ
     if (crank == 0 && warp < GJ_WARPS) gj_blocked(&Xs[0][0], Wb8, nbp, errflag, warp, lane);
-#else
-    if (crank == 0 && warp < GJ_WARPS) {
-        const int c0 = warp * GJ_COLS;
-        double X[GJ_COLS];
-#pragma unroll
-        for (int i = 0; i < GJ_COLS; ++i) X[i] = Xs[lane][c0 + i];
-        double s = Ss[lane];
-        double RD = 0.0;
-        double dcur = D0, rd = 1.0 / dcur;     // d_p and 1/d_p of the current step, identical in every thread
-        // state before step 0, published like the end of a step
-        if (lane == 0) {
-            double2 *dst = reinterpret_cast<double2 *>(&Row[0][c0]);
-#pragma unroll
-            for (int i = 0; i < GJ_COLS / 2; ++i) dst[i] = make_double2(X[2 * i], X[2 * i + 1]);
-        }
-        if (warp == 0) { Col[0][lane] = X[0]; Sv[0][lane] = s; }
-        Ps[0][warp][lane] = gj_tail_sum(X, 2 - c0);
-#ifdef NGT_PANEL_CLOCKS
-        long long gj_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, gj_last = clock64();
-#endif
-#pragma unroll 1
-        for (int p = 0; p < nbp; ++p) {
-            gj_barrier();
-            NGT_GJ_T(0);
-            const int b = p & 1, nb = b ^ 1;
-            const int p1 = min(p + 1, NB_INNER - 1);
-            // hand-over of state p-1: pivot row (own columns), pivot column (own row), s of the pivot row
-            double xp[GJ_COLS];
-            {
-                const double2 *src = reinterpret_cast<const double2 *>(&Row[b][c0]);
-#pragma unroll
-                for (int i = 0; i < GJ_COLS / 2; ++i) { const double2 v = src[i]; xp[2 * i] = v.x; xp[2 * i + 1] = v.y; }
-            }
-            const double colv = Col[b][lane];
-            const double sp = Sv[b][p];
-            NGT_GJ_T(1);
-            // next pivot, one step ahead (see header)
-            const double A = ((Ps[b][0][p1] + Ps[b][1][p1]) + (Ps[b][2][p1] + Ps[b][3][p1])) + Sv[b][p1];
-            const double B = ((Ps[b][0][p] + Ps[b][1][p]) + (Ps[b][2][p] + Ps[b][3][p])) + sp;
-            const double cn = Col[b][p1];
-            const double fn = (cn == 0.0) ? 0.0 : cn * rd;
-            const double dn = fma(fn, B, A);
-            const double rdn = 1.0 / dn;
-            NGT_GJ_T(2);
-            if (threadIdx.x == 0 && (!(dcur > 0.0) || isinf(dcur))) atomicOr(errflag, 1);
-            if (lane == p) RD = rd;
-            // eliminate pivot p from every row; rows that do not reach p stay clean even if d_p == 0
-            const double f = (lane == p || colv == 0.0) ? 0.0 : colv * rd;
-#pragma unroll
-            for (int i = 0; i < GJ_COLS; ++i) X[i] = fma(f, xp[i], X[i]);
-            s = fma(f, sp, s);
-            if (warp == (p >> 3)) gj_set(X, p & 7, (lane == p) ? 1.0 : f);   // column p joins the inverse
-            NGT_GJ_T(3);
-            // publish state p for step p+1 (row p+1, column p+1, s) and step p+2 (partial sums past column p+2)
-            if (lane == p + 1) {
-                double2 *dst = reinterpret_cast<double2 *>(&Row[nb][c0]);
-#pragma unroll
-                for (int i = 0; i < GJ_COLS / 2; ++i) dst[i] = make_double2(X[2 * i], X[2 * i + 1]);
-            }
-            if (warp == (p1 >> 3)) Col[nb][lane] = gj_get(X, p1 & 7);
-            if (warp == 0) Sv[nb][lane] = s;
-            Ps[nb][warp][lane] = gj_tail_sum(X, p + 3 - c0);
-            rd = rdn;
-            dcur = dn;
-            NGT_GJ_T(4);
-        }
-#ifdef NGT_PANEL_CLOCKS
-        if (threadIdx.x == 0 && blockIdx.x == 0)
-            for (int i = 0; i < 8; ++i) g_gj_clk[i] = gj_acc[i];
-#endif
-        NGT_CLK(2);
-        // W[u][q] = G[u][q] / d_u
-        if (lane >= nbp) RD = 0.0;
-#pragma unroll
-        for (int i = 0; i < GJ_COLS; ++i) Xs[lane][c0 + i] = (c0 + i < nbp) ? X[i] * RD : 0.0;
-    }
-#endif
+    NGT_CLK(2);
     __syncthreads();
     NGT_CLK(3);
     double *Wout = wbuf + ((long long)blockIdx.y * maxfb + slot + ko.wslot) * (NB_INNER * NB_INNER);

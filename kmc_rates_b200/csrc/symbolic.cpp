@@ -223,7 +223,6 @@ struct Dissector {
         unsigned hw = host_threads();
         max_par_depth = hw >= 16 ? 4 : hw >= 8 ? 3 : hw >= 4 ? 2 : hw >= 2 ? 1 : 0;
         if (const char *e = std::getenv("NGT_B200_ND_THREADS_DEPTH")) max_par_depth = std::atoi(e);
-        if (const char *e = std::getenv("NGT_B200_ND_BALANCE")) min_bal = std::atof(e);
     }
 
     // BFS from `start` over unvisited nodes (lvl < 0); appends to `visit`
@@ -493,8 +492,7 @@ void finish_layout(Symbolic &S) {
     // batches: per level, fronts with pivots, grouped by size class and capped for gridDim.y.  Fronts of one batch
     // share every launch, so the panel chains of same-level fronts run side by side; a wide class ratio keeps the
     // number of sequential chains per level small (grids are sized by the largest front, smaller ones exit early).
-    int size_class_ratio = 8;
-    if (const char *e = std::getenv("NGT_B200_CLASS_RATIO")) size_class_ratio = std::max(1, std::atoi(e));
+    const int size_class_ratio = 8;
     S.batches.clear();
     std::vector<std::vector<int32_t> > by_level(S.n_levels);
     for (int32_t i = 0; i < nf; ++i)

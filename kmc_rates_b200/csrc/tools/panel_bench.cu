@@ -61,13 +61,8 @@ int main(int argc, char **argv) {
         std::printf("  clocks: rowsum %lld  gauss-jordan %lld  sync %lld  W store %lld  row panel %lld\n", clk[1] - clk[0],
                     clk[2] - clk[1], clk[3] - clk[2], clk[4] - clk[3], clk[5] > clk[4] ? clk[5] - clk[4] : 0);
         CKB(cudaMemcpyFromSymbol(clk, ngt::g_gj_clk, sizeof(clk)));
-#ifdef NGT_OLD_GJ
-        std::printf("  gauss-jordan split (all steps): barrier %lld  loads %lld  look-ahead pivot %lld  update %lld  publish %lld\n",
-                    clk[0], clk[1], clk[2], clk[3], clk[4]);
-#else
         std::printf("  blocked gauss-jordan, warp 0, sum over the 4 block steps: 8x8 inversion %lld  barrier %lld  DMMA updates %lld  "
                     "closing barrier %lld\n", clk[0], clk[1], clk[2], clk[3]);
-#endif
     }
 #endif
     timeit("rowpanel (j=0)", [&] { ngt::launch_rowpanel(c, ids, 1, 0, f + 1 - 32); });
