@@ -169,6 +169,7 @@ struct NcclApi {
     int (*AllReduce)(const void *, void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void *, void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, comm_t, cudaStream_t) = nullptr;
+    int (*CommSplit)(comm_t, int, int, comm_t *, void *) = nullptr;   // NCCL >= 2.18; optional
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -191,6 +192,7 @@ struct NcclApi {
             a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
             a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(sym("ncclBroadcast"));
             a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
+            a.CommSplit = reinterpret_cast<decltype(a.CommSplit)>(dlsym(a.lib, "ncclCommSplit"));
             a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
             a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
             a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
@@ -211,8 +213,15 @@ struct NcclApi {
 // one communicator per process and GPU; the collectives run on the engine's own streams
 struct Comm {
     NcclApi::comm_t comm = nullptr;
+    // a clone of `comm` (ncclCommSplit) for the bulk panel broadcasts of the multi-GPU dense loop: they run on a third
+    // stream beside the owner's factorisation, and a communicator of their own keeps them out of the issue order of the
+    // small collectives on the main stream.  Null (older NCCL, world of one): everything goes through `comm`, in order.
+    NcclApi::comm_t comm2 = nullptr;
     int rank = 0, world = 1, device = 0;
-    ~Comm() { if (comm) NcclApi::get().CommDestroy(comm); }
+    ~Comm() {
+        if (comm2) NcclApi::get().CommDestroy(comm2);
+        if (comm) NcclApi::get().CommDestroy(comm);
+    }
 };
 
 using ngt::DFront;
@@ -374,6 +383,9 @@ struct Engine {
         for (auto &e : sync_ev)
             if (e) cudaEventDestroy(e);
         if (bulk_gate) cudaEventDestroy(bulk_gate);
+        if (ev_packed) cudaEventDestroy(ev_packed);
+        if (ev_rows) cudaEventDestroy(ev_rows);
+        if (stream3) { cudaStreamSynchronize(stream3); cudaStreamDestroy(stream3); }
         if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -412,6 +424,9 @@ struct Engine {
         CK(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, prio_lo));
         for (auto &x : sync_ev) CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&bulk_gate, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_packed, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_rows, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithPriority(&stream3, cudaStreamNonBlocking, prio_hi));
         for (auto &x : ev) CK(cudaEventCreate(&x));
         d_err.alloc(1);
         CK(cudaMemset(d_err.p, 0, sizeof(int)));
@@ -1131,8 +1146,15 @@ struct Engine {
         st.n_launches++;
     }
 
-    // owner: build the panel front from its own columns and factor it with the ordinary front kernels
-    void dist_factor_enqueue(int J) {
+    // owner: build the panel front from its own columns and factor it with the ordinary front kernels.
+    // stage 0 = everything (staged API); the NCCL loop runs 1 = pack, 2 = factor the square block, and the column-strip
+    // replay separately on every rank (dist_colstrip_enqueue)
+    void dist_colstrip_enqueue(int J) {
+        const int kb = block_end(J) - J, fr = S.fronts[0].f - J;
+        ngt::launch_dist_colstrip_slab(pan_buf(J) + W_DOUBLES, LD_PAN, kb, fr, stream);
+        st.n_launches++;
+    }
+    void dist_factor_enqueue(int J, int stage = 0) {
         const ngt::Front &F0 = S.fronts[0];
         const int JE = block_end(J), kb = JE - J, fr = F0.f - J;
         const int blk = J / ngt::NB_OUTER;
@@ -1143,7 +1165,8 @@ struct Engine {
         DFront P = h_dfronts[2 * blk];
         if (square) P.fr = kb;
         double *pan = pan_buf(J) + W_DOUBLES;
-        ngt::launch_dist_pack(d_pool.p + F0.off, F0.ld, J, kb, fr, pan, LD_PAN, d_spart.p, d_tauglob.p, stream);
+        if (stage != 2) ngt::launch_dist_pack(d_pool.p + F0.off, F0.ld, J, kb, fr, pan, LD_PAN, d_spart.p, d_tauglob.p, stream);
+        if (stage == 1) return;
         HostBatch hb;
         hb.ids = {2 * blk}; hb.f = {P.f}; hb.k = {P.k}; hb.fr = {P.fr}; hb.max_k = kb; hb.dev_off = 2 * blk;
         ngt::LaunchCtx c = ctx(d_pool.p, pool_stride, d_dfronts.p);
@@ -1166,7 +1189,7 @@ struct Engine {
         wslot_per_step = false;
         use_lookahead = la;
         d2_pending = pend;
-        if (square) { ngt::launch_dist_colstrip_slab(pan, LD_PAN, kb, fr, stream); st.n_launches++; }
+        if (square && stage == 0) dist_colstrip_enqueue(J);
         CK(cudaMemcpyAsync(pan_buf(J), d_wbuf.p, W_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice, stream));
     }
 
@@ -1262,6 +1285,8 @@ struct Engine {
         bulk_J = -1;
     }
     cudaEvent_t bulk_gate = nullptr;
+    cudaStream_t stream3 = nullptr;                  // bulk panel broadcasts of the multi-GPU dense loop
+    cudaEvent_t ev_packed = nullptr, ev_rows = nullptr;
 
     void dist_root_contrib_enqueue() {
         const ngt::Front &F0 = S.fronts[0];
@@ -1334,13 +1359,36 @@ struct Engine {
             NK(nc.AllReduce(d_spart.p, d_spart.p, (size_t)block, NcclApi::F64, NcclApi::SUM, cm.comm, stream));
             mark();
             const int owner = (J / block) % cm.world;
-            if (cm.rank == owner) dist_factor_enqueue(J);
-            dist_bulk_enqueue(true);      // the previous block's bulk update, if this rank held it back (see below)
-            mark();
+            const int kb = block_end(J) - J;
+            const bool split_bcast = opt.gemm_path == 0 && cm.world > 1;
             double *p = nullptr;
             int64_t cnt = 0;
             dist_panel(J, &p, &cnt);
-            NK(nc.Broadcast(p, p, (size_t)cnt, NcclApi::F64, owner, cm.comm, stream));
+            if (split_bcast) {
+                // The rows below the block (the bulk of the panel, up to 34 MB) travel RAW, on a third stream, while the
+                // owner factors the square block; afterwards only the factored block rows + W (0.6 MB) are broadcast
+                // and every rank replays the block's column operations on its copy of the rows below (39 us, instead
+                // of 120 us of broadcast behind 230 us of factorisation on everybody's critical path).
+                const size_t small_cnt = (size_t)W_DOUBLES + (size_t)kb * LD_PAN;
+                if (cm.rank == owner) dist_factor_enqueue(J, 1);                       // pack
+                CK(cudaEventRecord(ev_packed, stream));
+                CK(cudaStreamWaitEvent(stream3, ev_packed, 0));
+                if ((size_t)cnt > small_cnt)
+                    NK(nc.Broadcast(p + small_cnt, p + small_cnt, (size_t)cnt - small_cnt, NcclApi::F64, owner,
+                                    cm.comm2 ? cm.comm2 : cm.comm, stream3));
+                CK(cudaEventRecord(ev_rows, stream3));
+                if (cm.rank == owner) dist_factor_enqueue(J, 2);                       // factor the square block
+                dist_bulk_enqueue(true);      // the previous block's bulk update, if this rank held it back (see below)
+                mark();
+                NK(nc.Broadcast(p, p, small_cnt, NcclApi::F64, owner, cm.comm, stream));
+                CK(cudaStreamWaitEvent(stream, ev_rows, 0));
+                dist_colstrip_enqueue(J);
+            } else {
+                if (cm.rank == owner) dist_factor_enqueue(J);
+                dist_bulk_enqueue(true);
+                mark();
+                NK(nc.Broadcast(p, p, (size_t)cnt, NcclApi::F64, owner, cm.comm, stream));
+            }
             mark();
             // the rank that factors the next block keeps its bulk update out of that factorisation's way
             const bool next_owner = cm.world > 1 && J + block < (int)S.nI && cm.rank == ((J / block) + 1) % cm.world;
@@ -2237,6 +2285,7 @@ int ngt_comm_create(int32_t device, const uint8_t id[128], int32_t rank, int32_t
         NcclApi::unique_id u;
         std::memcpy(u.internal, id, 128);
         NK(NcclApi::get().CommInitRank(&c->comm, world, u, rank));
+        if (world > 1 && NcclApi::get().CommSplit) NK(NcclApi::get().CommSplit(c->comm, 0, rank, &c->comm2, nullptr));
         *out = reinterpret_cast<ngt_comm>(c.release());
     });
 }
