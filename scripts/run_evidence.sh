@@ -1,3 +1,5 @@
+# One-GPU evidence batch (run on the B200 box through gpurun): GPU tests, smoke, the ncu launch list of the config 2 step of
+# THIS build -> profiles/r02_traffic.json, then the bench line that quotes it.  Outputs under gpurun_out/final4/.
 set -x
 cd $GRAFT_REPO_ROOT
 O=gpurun_out/final4; mkdir -p $O

@@ -1,3 +1,4 @@
+# Multi-GPU batch (gpurun --gpus N): bench.py under torchrun at N ranks + scripts/nccl_check.py.  Outputs under gpurun_out/final_nN/.
 set -x
 cd $GRAFT_REPO_ROOT
 N=${1:-8}
