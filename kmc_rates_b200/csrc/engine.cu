@@ -1115,6 +1115,7 @@ struct Engine {
         d_dfronts.upload(h_dfronts);
         d_dids.upload(iota);
         d2_pending = false;
+        bulk_J = -1;                   // (a previous loop may have been abandoned on an error)
         if ((int)(ngt::NB_OUTER / ngt::NB_INNER) > maxfb) {
             // wbuf grows (one W per inner panel of an outer block): a step graph captured earlier has the old pointer
             // and stride baked in
