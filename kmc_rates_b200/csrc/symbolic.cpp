@@ -186,6 +186,12 @@ struct Sub {
 struct Dissector {
     int leaf;
     int max_par_depth;
+    // branches currently being dissected by some thread.  Below max_par_depth a split still forks when a core is free:
+    // the halves are uneven (min_bal), so with a fixed fork depth the largest depth-4 subtree (17k of 10^5 nodes) ran
+    // serially for ~11 ms after the other fifteen had finished.  The result does not depend on who forks (branches
+    // are appended in a fixed order).
+    std::atomic<int> running{1};
+    int hw_threads = 1;
     // smaller side of a split should hold at least this fraction.  Balanced trees cost more flops but fewer dependent
     // panel steps, and the GPU is latency-bound at the top of the tree: on the 10^5-minima landscape 0.25 / 0.30 /
     // 0.35 / 0.40 give 1.08 / 1.11 / 1.19 / 1.29e10 flops, 5.2 / 5.15 / 4.76 / 4.91 ms per step and 48 / 45 / 38 / 37 ms
@@ -221,29 +227,37 @@ struct Dissector {
 
     explicit Dissector(int leaf_) : leaf(leaf_) {
         unsigned hw = host_threads();
+        hw_threads = (int)hw;
         max_par_depth = hw >= 16 ? 4 : hw >= 8 ? 3 : hw >= 4 ? 2 : hw >= 2 ? 1 : 0;
         if (const char *e = std::getenv("NGT_B200_ND_THREADS_DEPTH")) max_par_depth = std::atoi(e);
     }
 
-    // BFS from `start` over unvisited nodes (lvl < 0); appends to `visit`
-    static void bfs(const Sub &G, int32_t start, std::vector<int32_t> &lvl, std::vector<int32_t> &visit, int32_t &nlev) {
+    // BFS from `start` over unvisited nodes; appends to `visit` and writes lvl[] of what it discovers.  The visited set
+    // is a bitmap (`seen`, one bit per node: 12 KB for 10^5 nodes, resident in L1) because ~19 of 20 adjacency entries
+    // lead to a node that is already visited, and that test was a miss in the 4-byte level array otherwise.
+    static void bfs(const Sub &G, int32_t start, std::vector<uint64_t> &seen, std::vector<int32_t> &lvl,
+                    std::vector<int32_t> &visit, int32_t &nlev) {
         size_t head = visit.size();
         visit.push_back(start);
         lvl[start] = 0;
+        seen[start >> 6] |= 1ull << (start & 63);
         nlev = 1;
         const int32_t *adj = G.adj.data();
-        const int32_t last = (int32_t)G.adj.size() - 1;
+        const int32_t *ptr = G.ptr.data();
+        uint64_t *bits = seen.data();
+        int32_t *lv = lvl.data();
         while (head < visit.size()) {
             const int32_t u = visit[head++];
-            const int32_t lu = lvl[u] + 1;
-            // the queue is known a few nodes ahead: pull the adjacency row of a later node and the level slots of
-            // this node's later neighbours towards the core (the sweep is a chain of dependent cache misses otherwise)
-            if (head + 4 < visit.size()) __builtin_prefetch(adj + G.ptr[visit[head + 4]]);
-            for (int32_t e = G.ptr[u]; e < G.ptr[u + 1]; ++e) {
-                __builtin_prefetch(&lvl[adj[std::min(e + 8, last)]]);
+            const int32_t lu = lv[u] + 1;
+            // the queue is known a few nodes ahead: pull the adjacency row of a later node towards the core
+            if (head + 4 < visit.size()) __builtin_prefetch(adj + ptr[visit[head + 4]]);
+            for (int32_t e = ptr[u], e1 = ptr[u + 1]; e < e1; ++e) {
                 const int32_t v = adj[e];
-                if (lvl[v] >= 0) continue;
-                lvl[v] = lu;
+                const uint64_t bit = 1ull << (v & 63);
+                uint64_t &w = bits[v >> 6];
+                if (w & bit) continue;
+                w |= bit;
+                lv[v] = lu;
                 nlev = lu + 1;
                 visit.push_back(v);
             }
@@ -326,6 +340,7 @@ struct Dissector {
         const auto t_enter = std::chrono::steady_clock::now();
         const int32_t n_enter = G.n;
         std::vector<int32_t> lvl, visit;
+        std::vector<uint64_t> seen;
         int32_t nlev = 0;
 
         // ---- first sweep: connectivity + a far node
@@ -337,7 +352,8 @@ struct Dissector {
         } else {
             lvl.assign(G.n, -1);
             visit.reserve(G.n);
-            bfs(G, 0, lvl, visit, nlev);
+            seen.assign(((size_t)G.n + 63) / 64, 0);
+            bfs(G, 0, seen, lvl, visit, nlev);
         }
         if ((int32_t)visit.size() != G.n) {
             // several components: small ones are packed into leaf-sized bins, large ones dissected on their own
@@ -346,7 +362,7 @@ struct Dissector {
             for (int32_t v = 0; v < G.n; ++v) {
                 if (lvl[v] >= 0) continue;
                 int32_t nl;
-                bfs(G, v, lvl, visit, nl);
+                bfs(G, v, seen, lvl, visit, nl);
                 comp_start.push_back((int32_t)visit.size());
             }
             std::vector<int32_t> bin, newid(G.n, -1);
@@ -377,9 +393,9 @@ struct Dissector {
                 if (d < bestdeg) { bestdeg = d; best = v; }
             }
             if (best != 0) {
-                std::fill(lvl.begin(), lvl.end(), -1);
+                seen.assign(((size_t)G.n + 63) / 64, 0);   // connected: the sweep rewrites every level
                 visit.clear();
-                bfs(G, best, lvl, visit, nlev);
+                bfs(G, best, seen, lvl, visit, nlev);
             }
         }
         if (nlev < 3) { out.emit_all(G); return; }   // no separator exists (e.g. a clique): one dense supernode
@@ -425,9 +441,13 @@ struct Dissector {
         if (trace && depth <= 5)
             std::fprintf(stderr, "[ngt timing]     dissect depth %d n %d sep %zu: sweeps+split %.2f ms\n", depth, n_enter, sep.size(),
                          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count());
-        if (depth < max_par_depth && P1.size() > 4096 && P2.size() > 4096) {
+        const bool fork = (depth < max_par_depth && P1.size() > 4096 && P2.size() > 4096) ||
+                          (max_par_depth > 0 && P1.size() > 1024 && P2.size() > 1024 &&
+                           running.load(std::memory_order_relaxed) < hw_threads);
+        if (fork) {
             // both halves are induced and dissected concurrently; G stays alive (read-only) until both are induced
             Out o2;
+            running.fetch_add(1, std::memory_order_relaxed);
             std::thread th([&] {
                 Sub H2;
                 {
@@ -435,6 +455,7 @@ struct Dissector {
                     induce(G, P2, newid, H2, team_threads(depth));
                 }
                 dissect(H2, o2, depth + 1);
+                running.fetch_sub(1, std::memory_order_relaxed);
             });
             {
                 Sub H1;
@@ -444,7 +465,9 @@ struct Dissector {
                 }
                 dissect(H1, out, depth + 1, &lvl1);
             }
+            running.fetch_sub(1, std::memory_order_relaxed);   // waiting is not running
             th.join();
+            running.fetch_add(1, std::memory_order_relaxed);
             G = Sub();
             out.append(o2);
         } else {
