@@ -53,7 +53,9 @@ typedef struct ngt_options {
     int32_t device;          /* CUDA device ordinal */
     int32_t gemm_path;       /* 0 = FP64 tensor-core DMMA, tile and feed (cp.async / TMA) chosen per launch (default); 1 = scalar DFMA (cross-check); 2 = DMMA with the plain 128x64 cp.async kernel everywhere (cross-check) */
     int32_t leaf_size;       /* nested-dissection leaf size (0 -> 64) */
-    int32_t reserved[13];    /* must be zero */
+    int32_t host_sweeps;     /* 1 = every level-structure sweep of the ordering on the host (cross-check); 0 = the sweeps of
+                                the largest subgraphs on the device (default; the ordering is the same either way) */
+    int32_t reserved[12];    /* must be zero */
 } ngt_options;
 
 /* ---- construction ------------------------------------------------------------------------- */
@@ -92,6 +94,9 @@ int ngt_get_rates(ngt_handle h, double out4[4]);                 /* k_AB, k_BA, 
 int ngt_get_final(ngt_handle h, double *omPxx, double *tau);      /* nbatch x (|A|+|B|) each, A then B in the order passed */
 int ngt_get_reduced(ngt_handle h, double *P, double *tau);        /* (|A|+|B|)^2 row-major, |A|+|B| */
 int ngt_get_initial_tau(ngt_handle h, double *tau);               /* n */
+/* node ids in elimination order: the intermediates, then A, then B (count = number of nodes named by a rate and not
+ * pruned); writes at most cap entries and the count */
+int ngt_get_elimination_order(ngt_handle h, int64_t *nodes, int64_t cap, int64_t *count);
 int ngt_get_committors(ngt_handle h, double *q);                  /* n; q_A = 0, q_B = 1 */
 int ngt_get_mfpt(ngt_handle h, double *t);                        /* n; mean first-passage time to A∪B */
 
@@ -171,6 +176,16 @@ int ngt_dist_finish(ngt_handle h);
  * Host pointers; labels has n entries. */
 int ngt_connected_components(int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, int32_t device,
                              int32_t *labels, int64_t *ncomp);
+
+/* ---- one level-structure sweep of the ordering on the device (diagnostic; csrc/ordering.cu) -------------------
+ * Breadth-first sweep of a connected, symmetric CSR graph (no self loops, no duplicate entries in a row) in the
+ * serial queue order.  start >= 0: from that node; start < 0: from node 0, then again from the minimum-degree node of
+ * the last level unless that is node 0 (the pseudo-peripheral step of the nested dissection, symbolic.cpp).
+ * Returns NGT_OK with *handled = 1 and lvl[n], visit[n], *nlev filled, or *handled = 0 when the kernel declines
+ * (graph not connected, levels thinner than ~24 nodes on average, a level above ~5000 nodes, n above ~1.5e6): the
+ * analysis sweeps such graphs on the host.  Host pointers. */
+int ngt_level_sweep(int32_t device, int32_t n, const int32_t *ptr, const int32_t *adj, int32_t start, int32_t *lvl,
+                    int32_t *visit, int32_t *nlev, int32_t *handled);
 
 /* ---- PATHSAMPLE ingest on the device (reference kmc_rates/utils.py:29-95) ---------------------
  * Rate constants of a min.data / ts.data database: mindata is nmin x 3 (energy, fvib, point-group order), tsdata

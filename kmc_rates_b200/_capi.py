@@ -25,7 +25,8 @@ class Options(ctypes.Structure):
         ("device", ctypes.c_int32),
         ("gemm_path", ctypes.c_int32),
         ("leaf_size", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 13),
+        ("host_sweeps", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 12),
     ]
 
 
@@ -85,6 +86,10 @@ def lib():
         "ngt_get_final": [H, _f64p, _f64p],
         "ngt_get_reduced": [H, _f64p, _f64p],
         "ngt_get_initial_tau": [H, _f64p],
+        "ngt_get_elimination_order": [H, _i64p, i64, _i64p],
+        "ngt_level_sweep": [ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                            ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                            ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)],
         "ngt_get_committors": [H, _f64p],
         "ngt_get_mfpt": [H, _f64p],
         "ngt_get_stats": [H, ctypes.POINTER(Stats)],
@@ -135,7 +140,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "ngt_create", "ngt_create_dense", "ngt_create_dense_dev", "ngt_set_rates", "ngt_set_rates_dev", "ngt_set_weights",
     "ngt_destroy", "ngt_compute_rates", "ngt_compute_rates_and_committors", "ngt_phase_one", "ngt_phase_two",
-    "ngt_get_rates", "ngt_get_final", "ngt_get_reduced", "ngt_get_initial_tau", "ngt_get_committors", "ngt_get_mfpt",
+    "ngt_get_rates", "ngt_get_final", "ngt_get_reduced", "ngt_get_initial_tau", "ngt_get_elimination_order", "ngt_level_sweep", "ngt_get_committors", "ngt_get_mfpt",
     "ngt_get_stats", "ngt_timed_steps", "ngt_profile_schur", "ngt_batch_create", "ngt_batch_create_dense", "ngt_batch_create_dense_dev", "ngt_batch_get_rates",
     "ngt_reduced_block_dev", "ngt_phase_two_shard", "ngt_set_final", "ngt_final_dev", "ngt_adopt_final_dev", "ngt_dist_begin", "ngt_dist_info", "ngt_dist_rowsum",
     "ngt_dist_factor", "ngt_dist_panel", "ngt_dist_apply", "ngt_dist_root", "ngt_dist_finish", "ngt_trim_device_cache",
@@ -178,6 +183,23 @@ def connected_components(n, src, dst, device=0):
     check(lib().ngt_connected_components(int(n), src.size, src.ctypes.data_as(_i64p), dst.ctypes.data_as(_i64p), int(device),
                                          labels.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.byref(ncomp)))
     return ncomp.value, labels
+
+
+def level_sweep(ptr, adj, start=-1, device=0):
+    """One level-structure sweep of the ordering on the device (include/ngt_b200.h, ngt_level_sweep): returns
+    (lvl, visit, nlev), or None when the kernel declines the graph."""
+    ptr = np.ascontiguousarray(ptr, np.int32)
+    adj = np.ascontiguousarray(adj, np.int32)
+    n = ptr.size - 1
+    lvl = np.empty(n, np.int32)
+    visit = np.empty(n, np.int32)
+    nlev = ctypes.c_int32()
+    handled = ctypes.c_int32()
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    check(lib().ngt_level_sweep(int(device), n, ptr.ctypes.data_as(i32p), adj.ctypes.data_as(i32p), int(start),
+                                lvl.ctypes.data_as(i32p), visit.ctypes.data_as(i32p), ctypes.byref(nlev),
+                                ctypes.byref(handled)))
+    return (lvl, visit, nlev.value) if handled.value else None
 
 
 def pathsample_rates(mindata, tsdata, m1, m2, T, device=0):
@@ -257,9 +279,9 @@ class Handle(object):
         self.nbatch = 1
 
     @staticmethod
-    def _opt(device=0, gemm_path=0, leaf_size=0):
+    def _opt(device=0, gemm_path=0, leaf_size=0, host_sweeps=0):
         o = Options()
-        o.device, o.gemm_path, o.leaf_size = int(device), int(gemm_path), int(leaf_size)
+        o.device, o.gemm_path, o.leaf_size, o.host_sweeps = int(device), int(gemm_path), int(leaf_size), int(host_sweeps)
         return o
 
     @classmethod
@@ -403,6 +425,14 @@ class Handle(object):
         P, tau = np.zeros((m, m)), np.zeros(m)
         check(lib().ngt_get_reduced(self.h, P.ctypes.data_as(_f64p), tau.ctypes.data_as(_f64p)))
         return P, tau
+
+    def elimination_order(self):
+        """node ids in elimination order (intermediates, then A, then B)"""
+        cnt = ctypes.c_int64()
+        check(lib().ngt_get_elimination_order(self.h, None, 0, ctypes.byref(cnt)))
+        out = np.empty(cnt.value, np.int64)
+        check(lib().ngt_get_elimination_order(self.h, out.ctypes.data_as(_i64p), out.size, ctypes.byref(cnt)))
+        return out
 
     def initial_tau(self):
         t = np.zeros(self.n)

@@ -9,6 +9,7 @@
 // There is no CPU compute path: every numeric step is a CUDA kernel from kernels.cu.
 #include "../../include/ngt_b200.h"
 #include "kernels.cuh"
+#include "ordering.h"
 #include "symbolic.h"
 
 #include <cuda.h>
@@ -1668,8 +1669,10 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
             }
         }
     });
+    // the sweeps of the largest subgraphs of the dissection run on the device (ordering.cu)
+    ngt::SweepAccel *accel = E->opt.host_sweeps ? nullptr : ngt::gpu_sweeps(E->opt.device);
     try {
-        ngt::analyse_sparse(g, present, E->A, E->B, E->opt.leaf_size, E->S);
+        ngt::analyse_sparse(g, present, E->A, E->B, E->opt.leaf_size, E->S, accel);
     } catch (...) {
         sweep.join();
         throw;
@@ -1682,7 +1685,7 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
         tm.lap("analysis (reachability sweep alongside)");
         if (pruned) {
             E->S = Symbolic();
-            ngt::analyse_sparse(g, present, E->A, E->B, E->opt.leaf_size, E->S);
+            ngt::analyse_sparse(g, present, E->A, E->B, E->opt.leaf_size, E->S, accel);
             tm.lap("analysis repeated on the pruned node set");
         }
     }
@@ -2105,6 +2108,16 @@ int ngt_get_initial_tau(ngt_handle h, double *tau) {
     });
 }
 
+int ngt_get_elimination_order(ngt_handle h, int64_t *nodes, int64_t cap, int64_t *count) {
+    return guard([&] {
+        Engine *E = eng(h);
+        const std::vector<int32_t> &na = E->S.node_at;
+        if (count) *count = (int64_t)na.size();
+        if (nodes)
+            for (int64_t i = 0; i < cap && i < (int64_t)na.size(); ++i) nodes[i] = na[i];
+    });
+}
+
 static int get_x(ngt_handle h, double *out, int which) {
     return guard([&] {
         Engine *E = eng_single(h, which == 0 ? "ngt_get_committors" : "ngt_get_mfpt");
@@ -2123,8 +2136,8 @@ int ngt_get_stats(ngt_handle h, ngt_stats *st) {
     return guard([&] {
         Engine *E = eng(h);
         *st = E->st;
-        st->reserved[2] = (double)g_h2d_bytes.load();   // process-wide byte counters (differences are what matter)
-        st->reserved[3] = (double)g_d2h_bytes.load();
+        st->reserved[2] = (double)(g_h2d_bytes.load() + ngt::gpu_sweeps_h2d_bytes());   // process-wide byte counters
+        st->reserved[3] = (double)(g_d2h_bytes.load() + ngt::gpu_sweeps_d2h_bytes());   // (differences are what matter)
     });
 }
 
@@ -2186,6 +2199,7 @@ int ngt_profile_schur(ngt_handle h, double *ms_schur, double *flops, int64_t *la
 
 void ngt_trim_device_cache(void) {
     g_cache.trim();
+    ngt::release_gpu_sweeps();
     trim_host_workspace();
 }
 
@@ -2221,6 +2235,19 @@ int ngt_dist_info(ngt_handle h, int64_t *n_pivots, int64_t *block) {
     return guard([&] {
         *n_pivots = eng(h)->S.nI;
         *block = ngt::NB_OUTER;
+    });
+}
+
+int ngt_level_sweep(int32_t device, int32_t n, const int32_t *ptr, const int32_t *adj, int32_t start, int32_t *lvl,
+                    int32_t *visit, int32_t *nlev, int32_t *handled) {
+    return guard([&] {
+        if (n < 1 || !ptr || !adj || !lvl || !visit || !nlev || !handled || start >= n) throw InvalidError("bad argument");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw CudaError("no CUDA device — kmc_rates_b200 has no CPU fallback");
+        if (device < 0 || device >= ndev) throw InvalidError("device ordinal out of range");
+        ngt::SweepAccel *accel = ngt::gpu_sweeps(device);
+        *handled = accel && accel->sweep(n, ptr, adj, (int64_t)ptr[n], start, lvl, visit, nlev) ? 1 : 0;
     });
 }
 

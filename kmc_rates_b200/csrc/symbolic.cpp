@@ -192,6 +192,25 @@ struct Dissector {
     // are appended in a fixed order).
     std::atomic<int> running{1};
     int hw_threads = 1;
+    // sweeps of large subgraphs go to the accelerator when the engine supplied one (same queue order, so the same
+    // ordering); a graph it keeps declining (not connected, thin levels) stops being offered
+    SweepAccel *accel = nullptr;
+    std::atomic<int> accel_declined{0};
+    bool offer(const Sub &G) const {
+        return accel && G.n >= accel->min_nodes && accel_declined.load(std::memory_order_relaxed) < 2;
+    }
+    bool accel_sweep(const Sub &G, int32_t start, std::vector<int32_t> &lvl, std::vector<int32_t> &visit, int32_t &nlev) {
+        lvl.resize(G.n);
+        visit.resize(G.n);
+        int32_t nl = 0;
+        if (accel->sweep(G.n, G.ptr.data(), G.adj.data(), (int64_t)G.adj.size(), start, lvl.data(), visit.data(), &nl)) {
+            nlev = nl;
+            return true;
+        }
+        accel_declined.fetch_add(1, std::memory_order_relaxed);
+        visit.clear();
+        return false;
+    }
     // smaller side of a split should hold at least this fraction.  Balanced trees cost more flops but fewer dependent
     // panel steps, and the GPU is latency-bound at the top of the tree: on the 10^5-minima landscape 0.25 / 0.30 /
     // 0.35 / 0.40 give 1.08 / 1.11 / 1.19 / 1.29e10 flops, 5.2 / 5.15 / 4.76 / 4.91 ms per step and 48 / 45 / 38 / 37 ms
@@ -344,13 +363,17 @@ struct Dissector {
         int32_t nlev = 0;
 
         // ---- first sweep: connectivity + a far node
+        bool swept = false;    // lvl / visit already hold the level structure rooted at the pseudo-peripheral node
         if (known_lvl && (int32_t)known_lvl->size() == G.n) {
             lvl = *known_lvl;
             visit.resize(G.n);
             for (int32_t i = 0; i < G.n; ++i) visit[i] = i;
             nlev = lvl.back() + 1;
+        } else if (offer(G) && accel_sweep(G, -1, lvl, visit, nlev)) {
+            swept = true;      // both sweeps done there (a graph that is not connected is declined)
         } else {
             lvl.assign(G.n, -1);
+            visit.clear();
             visit.reserve(G.n);
             seen.assign(((size_t)G.n + 63) / 64, 0);
             bfs(G, 0, seen, lvl, visit, nlev);
@@ -383,7 +406,7 @@ struct Dissector {
             return;
         }
         // ---- second sweep from a min-degree node of the last level (pseudo-peripheral, George & Liu)
-        {
+        if (!swept) {
             int32_t best = visit.back();
             int32_t bestdeg = G.ptr[best + 1] - G.ptr[best];
             for (size_t i = visit.size(); i-- > 0;) {
@@ -392,9 +415,10 @@ struct Dissector {
                 const int32_t d = G.ptr[v + 1] - G.ptr[v];
                 if (d < bestdeg) { bestdeg = d; best = v; }
             }
-            if (best != 0) {
+            if (best != 0 && !(offer(G) && accel_sweep(G, best, lvl, visit, nlev))) {
                 seen.assign(((size_t)G.n + 63) / 64, 0);   // connected: the sweep rewrites every level
                 visit.clear();
+                visit.reserve(G.n);
                 bfs(G, best, seen, lvl, visit, nlev);
             }
         }
@@ -644,7 +668,7 @@ void analyse_dense(int64_t n, const std::vector<int64_t> &A, const std::vector<i
 
 void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
                     const std::vector<int64_t> &A, const std::vector<int64_t> &B,
-                    int leaf_size, Symbolic &S) {
+                    int leaf_size, Symbolic &S, SweepAccel *accel) {
     S = Symbolic();
     const int64_t n = g.n;
     S.n = n;
@@ -661,6 +685,7 @@ void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
     S.nI = (int64_t)inter.size();
     Timer tm;
     Dissector D(leaf_size > 0 ? leaf_size : 64);
+    D.accel = accel;
     // top-level subgraph: the rate graph induced on the intermediates (A ∪ B and absent nodes are left out, so
     // the dissector never walks through them)
     Sub top;

@@ -106,12 +106,28 @@ struct IndexScratch {
 void index_edges(int64_t n, int64_t nnz, const int64_t *src, const int64_t *dst, EdgeIndex &ix, Adjacency &g,
                  IndexScratch *ws = nullptr);
 
+// Optional accelerator for the level-structure sweeps of large subgraphs (the engine installs a CUDA kernel,
+// ordering.cu).  A sweep is a breadth-first search that reports the serial queue order exactly: level L + 1 lists the
+// nodes in the order (position of the first discovering parent in level L, position in that parent's row), so the
+// ordering does not depend on who sweeps.
+struct SweepAccel {
+    virtual ~SweepAccel() = default;
+    // CSR subgraph (local ids, symmetric, no self loops, rows without duplicates).
+    // start >= 0: one sweep from `start`.  start < 0: pseudo-peripheral search -- sweep from node 0, pick the
+    // minimum-degree node of the last level (the latest visited among equals) and, unless that is node 0, sweep again
+    // from it.  Fills lvl[n], visit[n], *nlev and returns true; returns false when it declines (size limits, no free
+    // context, graph not connected, levels too thin to pay off, device error): the caller sweeps on the host.
+    virtual bool sweep(int32_t n, const int32_t *ptr, const int32_t *adj, int64_t nadj, int32_t start, int32_t *lvl,
+                       int32_t *visit, int32_t *nlev) = 0;
+    int32_t min_nodes = 24576;   // smaller subgraphs are swept on the host (copy + launch cost more than the sweep)
+};
+
 // Sparse network: nested dissection + supernodal symbolic factorisation.
 // present[u] = 0 marks ids that appear in no rate (they are ignored, like the reference which only
 // creates nodes named by a rate, ngt.hpp:114-117).
 void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
                     const std::vector<int64_t> &A, const std::vector<int64_t> &B,
-                    int leaf_size, Symbolic &S);
+                    int leaf_size, Symbolic &S, SweepAccel *accel = nullptr);
 
 // Complete network: one front holding every intermediate, plus the root.
 void analyse_dense(int64_t n, const std::vector<int64_t> &A, const std::vector<int64_t> &B, Symbolic &S);

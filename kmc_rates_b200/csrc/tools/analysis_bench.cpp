@@ -1,6 +1,6 @@
 // Host-only timing harness for the symbolic analysis (no CUDA needed):
 //   g++ -O3 -std=c++17 -pthread -I.. analysis_bench.cpp ../symbolic.cpp -o /tmp/analysis_bench
-//   NGT_B200_TIMING=1 /tmp/analysis_bench graph.bin [reps]
+//   NGT_B200_TIMING=1 /tmp/analysis_bench graph.bin [reps [leaf_size]]
 // graph.bin: int64 n, int64 nnz, int64 nA, int64 nB, src[nnz], dst[nnz], A[nA], B[nB]   (see scripts/dump_graph.py)
 #include <chrono>
 #include <cstdio>
@@ -22,6 +22,7 @@ int main(int argc, char **argv) {
         return 1;
     std::fclose(fp);
     const int reps = argc > 2 ? std::atoi(argv[2]) : 3;
+    const int leaf = argc > 3 ? std::atoi(argv[3]) : 0;
     for (int r = 0; r < reps; ++r) {
         auto t0 = std::chrono::steady_clock::now();
         ngt::EdgeIndex ix;
@@ -29,7 +30,7 @@ int main(int argc, char **argv) {
         ngt::index_edges(n, nnz, src.data(), dst.data(), ix, g);
         auto t1 = std::chrono::steady_clock::now();
         ngt::Symbolic S;
-        ngt::analyse_sparse(g, ix.present, A, B, 0, S);
+        ngt::analyse_sparse(g, ix.present, A, B, leaf, S);
         auto t2 = std::chrono::steady_clock::now();
         unsigned long long hsh = 1469598103934665603ULL;   // FNV-1a over the elimination order
         for (int32_t v : S.node_at) { hsh ^= (unsigned long long)(unsigned)v; hsh *= 1099511628211ULL; }

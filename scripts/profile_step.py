@@ -20,10 +20,11 @@ ap.add_argument("nbatch", nargs="?", type=int, default=0)
 ap.add_argument("--warmup", type=int, default=1)
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--gemm", type=int, default=0)
+ap.add_argument("--leaf", type=int, default=0, help="nested-dissection leaf size (0 = the default, 64)")
 a = ap.parse_args()
 if a.workload == "c2":
     n, src, dst, k, A, B = synth.landscape_2d(a.size or 316, T=0.3, seed=0)
-    h = Handle.from_coo(n, src, dst, k, A, B, gemm_path=a.gemm)
+    h = Handle.from_coo(n, src, dst, k, A, B, gemm_path=a.gemm, leaf_size=a.leaf)
 elif a.workload == "c4":
     n, src, dst, k, A, B = synth.landscape_groups(141, 512, 512, T=0.3, seed=0)
     h = Handle.from_coo(n, src, dst, k, A, B, gemm_path=a.gemm)
