@@ -55,7 +55,8 @@ typedef struct ngt_options {
     int32_t leaf_size;       /* nested-dissection leaf size (0 -> 64) */
     int32_t host_sweeps;     /* 1 = every level-structure sweep of the ordering on the host (cross-check); 0 = the sweeps of
                                 the largest subgraphs on the device (default; the ordering is the same either way) */
-    int32_t reserved[12];    /* must be zero */
+    int32_t sweep_min_nodes; /* subgraphs of the ordering with at least this many nodes are swept on the device (0 -> 65536) */
+    int32_t reserved[11];    /* must be zero */
 } ngt_options;
 
 /* ---- construction ------------------------------------------------------------------------- */
@@ -182,7 +183,7 @@ int ngt_connected_components(int64_t n, int64_t nnz, const int64_t *src, const i
  * serial queue order.  start >= 0: from that node; start < 0: from node 0, then again from the minimum-degree node of
  * the last level unless that is node 0 (the pseudo-peripheral step of the nested dissection, symbolic.cpp).
  * Returns NGT_OK with *handled = 1 and lvl[n], visit[n], *nlev filled, or *handled = 0 when the kernel declines
- * (graph not connected, levels thinner than ~24 nodes on average, a level above ~5000 nodes, n above ~1.5e6): the
+ * (graph not connected, levels thinner than ~24 nodes on average, a level above 16384 nodes, n above ~1.4e6): the
  * analysis sweeps such graphs on the host.  Host pointers. */
 int ngt_level_sweep(int32_t device, int32_t n, const int32_t *ptr, const int32_t *adj, int32_t start, int32_t *lvl,
                     int32_t *visit, int32_t *nlev, int32_t *handled);

@@ -26,7 +26,8 @@ class Options(ctypes.Structure):
         ("gemm_path", ctypes.c_int32),
         ("leaf_size", ctypes.c_int32),
         ("host_sweeps", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 12),
+        ("sweep_min_nodes", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 11),
     ]
 
 
@@ -279,9 +280,10 @@ class Handle(object):
         self.nbatch = 1
 
     @staticmethod
-    def _opt(device=0, gemm_path=0, leaf_size=0, host_sweeps=0):
+    def _opt(device=0, gemm_path=0, leaf_size=0, host_sweeps=0, sweep_min_nodes=0):
         o = Options()
         o.device, o.gemm_path, o.leaf_size, o.host_sweeps = int(device), int(gemm_path), int(leaf_size), int(host_sweeps)
+        o.sweep_min_nodes = int(sweep_min_nodes)
         return o
 
     @classmethod

@@ -1607,10 +1607,23 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
             emit(e);
         }
     };
+    // the sweeps of the largest subgraphs of the dissection run on the device (ordering.cu); the first of them is on
+    // the critical path of the whole build, so the bulk copies below wait until its subgraph has gone up (they have
+    // ~30 ms of analysis to hide behind, and two pageable copies at once halve each other's rate)
+    ngt::SweepAccel *accel = E->opt.host_sweeps ? nullptr : ngt::gpu_sweeps(E->opt.device);
+    const int32_t sweep_min = E->opt.sweep_min_nodes > 0 ? E->opt.sweep_min_nodes : (accel ? accel->min_nodes : 0);
+    const int uploads_before = accel ? accel->uploads.load(std::memory_order_acquire) : 0;
+    std::atomic<bool> analysis_done{false};
     SideTask device_task, count_task;
     device_task.start([&] {
         E->init_device();
         E->d_k.alloc((size_t)nnz * E->nbatch);
+        if (accel && n >= sweep_min) {
+            const auto t_gate = std::chrono::steady_clock::now();
+            while (accel->uploads.load(std::memory_order_acquire) == uploads_before && !analysis_done.load(std::memory_order_acquire) &&
+                   std::chrono::steady_clock::now() - t_gate < std::chrono::milliseconds(8))
+                std::this_thread::sleep_for(std::chrono::microseconds(100));
+        }
         if (k) {
             CK(cudaMemcpy(E->d_k.p, k, (size_t)nnz * E->nbatch * sizeof(double), cudaMemcpyHostToDevice));
             g_h2d_bytes += (long long)((size_t)nnz * E->nbatch * sizeof(double));
@@ -1669,14 +1682,14 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
             }
         }
     });
-    // the sweeps of the largest subgraphs of the dissection run on the device (ordering.cu)
-    ngt::SweepAccel *accel = E->opt.host_sweeps ? nullptr : ngt::gpu_sweeps(E->opt.device);
     try {
-        ngt::analyse_sparse(g, present, E->A, E->B, E->opt.leaf_size, E->S, accel);
+        ngt::analyse_sparse(g, present, E->A, E->B, E->opt.leaf_size, E->S, accel, sweep_min);
     } catch (...) {
+        analysis_done.store(true, std::memory_order_release);
         sweep.join();
         throw;
     }
+    analysis_done.store(true, std::memory_order_release);
     sweep.join();
     {
         bool pruned = false;
@@ -1685,7 +1698,7 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
         tm.lap("analysis (reachability sweep alongside)");
         if (pruned) {
             E->S = Symbolic();
-            ngt::analyse_sparse(g, present, E->A, E->B, E->opt.leaf_size, E->S, accel);
+            ngt::analyse_sparse(g, present, E->A, E->B, E->opt.leaf_size, E->S, accel, sweep_min);
             tm.lap("analysis repeated on the pruned node set");
         }
     }
@@ -2247,7 +2260,7 @@ int ngt_level_sweep(int32_t device, int32_t n, const int32_t *ptr, const int32_t
             throw CudaError("no CUDA device — kmc_rates_b200 has no CPU fallback");
         if (device < 0 || device >= ndev) throw InvalidError("device ordinal out of range");
         ngt::SweepAccel *accel = ngt::gpu_sweeps(device);
-        *handled = accel && accel->sweep(n, ptr, adj, (int64_t)ptr[n], start, lvl, visit, nlev) ? 1 : 0;
+        *handled = accel && accel->sweep(n, ptr, adj, (int64_t)ptr[n], start, lvl, visit, nlev) == 1 ? 1 : 0;
     });
 }
 

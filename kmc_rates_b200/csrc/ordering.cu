@@ -1,14 +1,14 @@
 // Level-structure sweeps of the nested-dissection ordering on the GPU (see ordering.h, symbolic.h: SweepAccel).
 //
-// One CTA of 1024 threads walks the whole subgraph level by level.  The visited set is a bitmap in shared memory
-// (n / 8 bytes), so the ~19 of 20 adjacency entries that lead to a visited node cost one shared-memory read.  The
-// sweep reports the serial breadth-first queue order exactly: the serial sweep appends a node at its first sighting,
-// i.e. at the smallest (position of the parent in its level, position in the parent's row) among the entries that
-// lead to it, so every entry (p, j) of the frontier that leads to an unvisited node v claims it with
-// atomicMin(key[v], p << 32 | j), the claim that stands is the winner, and winners are placed at (exclusive scan of
-// the winners per parent) + (rank inside the parent's row).  See sw_run for the phases.
-// A level costs a few dependent L2 round trips plus ~20 warp instructions per frontier node, against ~2.6 ns per
-// adjacency entry on a host core; the kernel gives up (status 2) on structures thinner than ~24 nodes per level.
+// A cluster of eight CTAs walks the whole subgraph level by level.  Every CTA keeps the visited set as a bitmap in its
+// shared memory (n / 8 bytes), so the ~19 of 20 adjacency entries that lead to a visited node cost one shared-memory
+// read.  The sweep reports the serial breadth-first queue order exactly: the serial sweep appends a node at its first
+// sighting, i.e. at the smallest (position of the parent in its level, position in the parent's row) among the entries
+// that lead to it, so every entry (p, j) of the frontier that leads to an unvisited node v claims it with
+// atomicMin(key[v], p << 18 | j), the claim that stands is the winner, and winners are placed at (exclusive scan of the
+// winners per parent) + (rank inside the parent's row).  See sw_run for the phases.
+// The kernel gives up (status 2) on structures thinner than ~24 nodes per level: a level costs it ~4 us whatever its
+// size, a host core ~2.6 ns per adjacency entry.
 #include "ordering.h"
 
 #include <cuda_runtime.h>
@@ -26,23 +26,30 @@
 namespace ngt {
 namespace {
 
-constexpr int SW_THREADS = 1024;
-constexpr int SW_FCAP_MAX = 7168;      // largest level the per-parent arrays are sized for (28 bytes per node, < 2^13)
+constexpr int SW_THREADS = 512;        // per CTA: 128 registers each, a whole row of <= 32 entries in flight
+constexpr int SW_CL = 8;               // CTAs of the cluster that walks one subgraph
+constexpr int SW_FCAP = 16384;         // largest level (its nodes' row extents live in global memory)
+constexpr int SW_LP = SW_FCAP / SW_CL; // largest slice of a level one CTA takes
+constexpr int SW_LT = 4096;            // most nodes one CTA's slice may win for the next level
+constexpr int SW_ROW = 32;             // row entries a thread keeps in flight
+constexpr int SW_JBITS = 18;           // claim = position of the parent in its level << 18 | position in the parent's row
 constexpr int SW_SMEM_LIMIT = 227 * 1024;
 
 struct SweepOut {
     int count;    // nodes reached by the last sweep
     int nlev;     // its number of levels
-    int status;   // 0 ok, 1 not connected, 2 levels too thin, 3 a level exceeded the shared-memory arrays, 4 internal
+    int status;   // 0 ok, 1 not connected, 2 levels too thin, 3 a level exceeded the arrays, 4 internal
     int root;     // start node of the last sweep
 #ifdef NGT_SW_CLOCKS
-    long long t[6];   // cycles of thread 0 in: init, A, B1, scan, B3, levels
+    long long t[12];  // cycles of thread 0 of CTA 0 per piece of a level (see SW_T), [11] = levels
 #endif
 };
 #ifdef NGT_SW_CLOCKS
-#define SW_T(i) do { if (threadIdx.x == 0) { const long long c_ = clock64(); a.out->t[i] += c_ - t_last; t_last = c_; } } while (0)
+#define SW_T(i) do { if (threadIdx.x == 0 && c == 0) { const long long c_ = clock64(); a.out->t[i] += c_ - t_last; t_last = c_; } } while (0)
+#define SW_TD(i, dep) do { if (threadIdx.x == 0 && c == 0) { const long long c_ = clock64() + ((dep) == -12345 ? 1 : 0); a.out->t[i] += c_ - t_last; t_last = c_; } } while (0)
 #else
 #define SW_T(i) do { } while (0)
+#define SW_TD(i, dep) do { } while (0)
 #endif
 
 struct SweepArgs {
@@ -55,22 +62,39 @@ struct SweepArgs {
     int *visit;
     SweepOut *out;
     int nw;       // bitmap words
-    int fcap;     // capacity of the per-parent counters
+    int *hr0;     // 2 x SW_FCAP: row start of the nodes of the current / next level (by level parity)
+    int *hdeg;    // 2 x SW_FCAP: their degrees
 };
 
 struct SweepSmem {
-    unsigned *bits;
-    int *r0, *deg;         // row start and degree of the current / next level's nodes (2 x fcap each, double buffered)
-    int *off;              // winners per parent, then their exclusive prefix sums
-    int *touched;          // the nodes of the next level, in the order their winners were found
-    unsigned *tkey;        // per touched node: parent << SW_JBITS | rank among the parent's winners
+    unsigned *bits;        // every CTA keeps the whole visited set
+    int *lr0, *ldeg;       // row start and degree of this CTA's slice of the level
+    int *off;              // winners per parent of the slice, then their exclusive prefix sums
+    int *touched;          // the nodes this CTA's slice won, in the order they were found
+    unsigned *tkey;        // per touched node: parent (index in the slice) << 19 | rank among the parent's winners
     int *wsum;             // 33
     int *ctr;              // 0: touched nodes
+    int *tot;              // 2 x SW_CL x 2: per level parity and CTA: nodes won, overflow flag (written by the peers)
     unsigned long long *best;
 };
-constexpr int SW_JBITS = 19;           // claim = parent position << 19 | position in the parent's row
 
 __device__ __forceinline__ bool sw_seen(const unsigned *bits, int v) { return (bits[v >> 5] >> (v & 31)) & 1u; }
+// all threads of all CTAs of the cluster; orders their global-memory accesses (release / acquire at cluster scope)
+__device__ __forceinline__ void sw_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store into the same shared-memory variable of CTA `cta` of the cluster
+__device__ __forceinline__ void sw_peer_store(int *mine, int cta, int value) {
+    const unsigned local = (unsigned)__cvta_generic_to_shared(mine);
+    unsigned remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(cta));
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(value) : "memory");
+}
+__device__ __forceinline__ int sw_cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return (int)r;
+}
 
 // exclusive prefix sums of x[0..n) in place; returns the total (uniform over the CTA)
 __device__ int sw_scan(int *x, int n, int *wsum) {
@@ -88,7 +112,7 @@ __device__ int sw_scan(int *x, int n, int *wsum) {
     if (lane == 31) wsum[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        const int w = wsum[lane];
+        const int w = lane < SW_THREADS / 32 ? wsum[lane] : 0;
         int winc = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -110,112 +134,151 @@ __device__ int sw_scan(int *x, int n, int *wsum) {
     return total;
 }
 
-// One sweep from `start`; every return value is uniform over the CTA.  One thread per node of the level (the
-// "parent") walks that node's row, four entries in flight:
-//   A  an entry (p, j) that leads to an unvisited node v claims it: atomicMin(key[v], p << 19 | j), no return value;
+// up to 32 consecutive entries of one row, all in flight: claims ...
+__device__ __forceinline__ void sw_claim_chunk(const SweepArgs &a, const SweepSmem &s, const int *src, int nvalid,
+                                               unsigned kbase) {
+    int v[SW_ROW];
+#pragma unroll
+    for (int t = 0; t < SW_ROW; ++t) v[t] = t < nvalid ? __ldg(src + t) : -1;
+#pragma unroll
+    for (int t = 0; t < SW_ROW; ++t)
+        if (v[t] >= 0 && !sw_seen(s.bits, v[t])) atomicMin(a.key + v[t], kbase + (unsigned)t);
+}
+// ... and winners (cnt: winners of this parent so far = rank of the next one)
+__device__ __forceinline__ void sw_win_chunk(const SweepArgs &a, const SweepSmem &s, const int *src, int nvalid,
+                                             unsigned kbase, int q, int &cnt) {
+    int v[SW_ROW];
+    unsigned k[SW_ROW];
+#pragma unroll
+    for (int t = 0; t < SW_ROW; ++t) {
+        v[t] = t < nvalid ? __ldg(src + t) : -1;
+        if (v[t] >= 0 && sw_seen(s.bits, v[t])) v[t] = -1;
+    }
+#pragma unroll
+    for (int t = 0; t < SW_ROW; ++t) k[t] = v[t] >= 0 ? __ldcg(a.key + v[t]) : 0u;
+#pragma unroll
+    for (int t = 0; t < SW_ROW; ++t)
+        if (v[t] >= 0 && k[t] == kbase + (unsigned)t) {
+            const int i = atomicAdd(s.ctr, 1);
+            if (i < SW_LT) {
+                s.touched[i] = v[t];
+                s.tkey[i] = ((unsigned)q << 19) | (unsigned)cnt;
+            }
+            ++cnt;
+        }
+}
+
+// One sweep from `start` by the whole cluster; every return value is uniform over the cluster.  A level's nodes (the
+// "parents") are split into SW_CL contiguous slices, one per CTA, one thread per parent, eight row entries in flight:
+//   A  an entry (p, j) that leads to an unvisited node v claims it: atomicMin(key[v], p << 18 | j), no return value;
 //   B  the same walk again: the entry whose claim stands is the winner.  A thread meets its parent's winners in row
-//      order, so the rank of a winner inside its parent is a running count; winners go on the `touched` list;
-//   C  exclusive scan of the winners per parent: every parent's offset in the next level;
-//   D  one thread per touched node: position = offset of its parent + rank; level, visited bit, row extent.
-// What bounds a level is the ~1.3 cycles the SM's memory pipe needs per scattered 32-bit atomic or load (about seven
-// claims and seven re-reads per new node), then the issue slots of 32 warps; a warp or eight lanes per parent cost
-// 5-10x the instructions, returning (64-bit) atomics twice the pipe time.
+//      order, so the rank of a winner inside its parent is a running count; winners go on the CTA's `touched` list;
+//   C  exclusive scan of the winners per parent inside the slice; the slices' totals are exchanged through global
+//      memory, which gives every CTA the offset of its slice in the next level;
+//   D  one thread per touched node: position = slice offset + parent offset + rank; level and row extent to global
+//      memory;
+//   E  every CTA sets the bits of the whole new level in its own copy of the visited set.
+// Three cluster barriers per level.  What bounds a level on one SM is the ~1.3 cycles its memory pipe needs per
+// scattered 32-bit atomic or load (about seven claims and seven re-reads per new node: 20 us per level of ~700 nodes,
+// no better than a host core); a warp or eight lanes per parent cost 5-10x the instructions, returning 64-bit atomics
+// twice the pipe time.  Eight SMs share that work.
 __device__ int sw_run(const SweepArgs &a, const SweepSmem &s, int start, int *count, int *nlev, int *last_base,
                       int *last_size) {
     const int tid = threadIdx.x;
+    const int c = sw_cluster_rank();
 #ifdef NGT_SW_CLOCKS
     long long t_last = clock64();
 #endif
     for (int i = tid; i < a.nw; i += SW_THREADS) s.bits[i] = 0u;
-    for (int i = tid; i < a.n; i += SW_THREADS) a.key[i] = ~0u;
+    for (int i = c * SW_THREADS + tid; i < a.n; i += SW_CL * SW_THREADS) a.key[i] = ~0u;
     if (tid == 0) {
-        a.visit[0] = start;
-        a.lvl[start] = 0;
-        const int r0 = __ldg(a.ptr + start);
-        s.r0[0] = r0;
-        s.deg[0] = __ldg(a.ptr + start + 1) - r0;
+        if (c == 0) {
+            a.visit[0] = start;
+            a.lvl[start] = 0;
+            const int r0 = __ldg(a.ptr + start);
+            a.hr0[0] = r0;
+            a.hdeg[0] = __ldg(a.ptr + start + 1) - r0;
+        }
         s.ctr[0] = 0;
     }
     __syncthreads();
     if (tid == 0) s.bits[start >> 5] |= 1u << (start & 31);
-    __syncthreads();
+    sw_cluster_sync();
     int base = 0, fsz = 1, level = 0, visited = 1;
     SW_T(0);
     for (;;) {
-        const int flip = (level & 1) ? a.fcap : 0;
-        const int *cr0 = s.r0 + flip, *cdeg = s.deg + flip;
-        int *nr0 = s.r0 + (a.fcap - flip), *ndeg = s.deg + (a.fcap - flip);
+        const int par = level & 1;
+        const int *chr0 = a.hr0 + par * SW_FCAP, *chdeg = a.hdeg + par * SW_FCAP;
+        int *nhr0 = a.hr0 + (par ^ 1) * SW_FCAP, *nhdeg = a.hdeg + (par ^ 1) * SW_FCAP;
+        const int lo = (int)((long long)fsz * c / SW_CL), hi = (int)((long long)fsz * (c + 1) / SW_CL);
+        const int np = hi - lo;
         // ---- A: claims
-        for (int p = tid; p < fsz; p += SW_THREADS) {
-            const int dg = cdeg[p];
-            const int *row = a.adj + cr0[p];
-            const unsigned kp = (unsigned)p << SW_JBITS;
-            for (int j = 0; j < dg; j += 4) {
-                int v[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) v[t] = j + t < dg ? __ldg(row + j + t) : -1;
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    if (v[t] >= 0 && !sw_seen(s.bits, v[t])) atomicMin(a.key + v[t], kp | (unsigned)(j + t));
-            }
+        for (int q = tid; q < np; q += SW_THREADS) {
+            const int r0 = __ldcg(chr0 + lo + q), dg = __ldcg(chdeg + lo + q);
+            s.lr0[q] = r0;
+            s.ldeg[q] = dg;
+            const unsigned kp = (unsigned)(lo + q) << SW_JBITS;
+            for (int j = 0; j < dg; j += SW_ROW)
+                sw_claim_chunk(a, s, a.adj + r0 + j, min(dg - j, SW_ROW), kp + (unsigned)j);
         }
-        __syncthreads();
-        SW_T(1);
-        // ---- B: winners, in row order per parent
-        for (int p = tid; p < fsz; p += SW_THREADS) {
-            const int dg = cdeg[p];
-            const int *row = a.adj + cr0[p];
-            const unsigned kp = (unsigned)p << SW_JBITS;
-            int cnt = 0;
-            for (int j = 0; j < dg; j += 4) {
-                int v[4];
-                unsigned k[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    v[t] = j + t < dg ? __ldg(row + j + t) : -1;
-                    if (v[t] >= 0 && sw_seen(s.bits, v[t])) v[t] = -1;
-                }
-#pragma unroll
-                for (int t = 0; t < 4; ++t) k[t] = v[t] >= 0 ? __ldcg(a.key + v[t]) : 0u;
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    if (v[t] >= 0 && k[t] == (kp | (unsigned)(j + t))) {
-                        const int i = atomicAdd(s.ctr, 1);
-                        if (i < a.fcap) {
-                            s.touched[i] = v[t];
-                            s.tkey[i] = kp | (unsigned)cnt;
-                        }
-                        ++cnt;
-                    }
-            }
-            s.off[p] = cnt;
-        }
-        __syncthreads();
-        SW_T(2);
-        const int nt = s.ctr[0];
-        if (nt > a.fcap) return 3;                           // the next level exceeds the shared-memory arrays
-        // ---- C: offsets of the parents in the next level
-        const int total = sw_scan(s.off, fsz, s.wsum);
-        if (tid == 0) s.ctr[0] = 0;                          // for the next level's B (two barriers away)
         SW_T(3);
-        if (total != nt) return 4;                           // cannot happen: every claimed node has one winner
+        sw_cluster_sync();
+        SW_T(4);
+        // ---- B: winners, in row order per parent
+        for (int q = tid; q < np; q += SW_THREADS) {
+            const int r0 = s.lr0[q], dg = s.ldeg[q];
+            const unsigned kp = (unsigned)(lo + q) << SW_JBITS;
+            int cnt = 0;
+            for (int j = 0; j < dg; j += SW_ROW)
+                sw_win_chunk(a, s, a.adj + r0 + j, min(dg - j, SW_ROW), kp + (unsigned)j, q, cnt);
+            s.off[q] = cnt;
+        }
+        __syncthreads();
+        SW_T(5);
+        // ---- C: offsets of the parents inside the slice, of the slice inside the next level
+        const int nt = s.ctr[0];
+        const int slice_total = sw_scan(s.off, np, s.wsum);
+        if (tid < SW_CL) {                                   // every CTA learns every slice's total (distributed shared memory)
+            sw_peer_store(s.tot + (par * SW_CL + c) * 2, tid, nt);
+            sw_peer_store(s.tot + (par * SW_CL + c) * 2 + 1, tid, (nt > SW_LT || slice_total != nt) ? 1 : 0);
+        }
+        if (tid == 0) s.ctr[0] = 0;                          // for the next level's B
+        SW_T(6);
+        sw_cluster_sync();
+        int slice_base = 0, total = 0, bad = 0;
+#pragma unroll
+        for (int cc = 0; cc < SW_CL; ++cc) {
+            const int t = s.tot[(par * SW_CL + cc) * 2];
+            bad |= s.tot[(par * SW_CL + cc) * 2 + 1];
+            if (cc < c) slice_base += t;
+            total += t;
+        }
+        SW_T(7);
+        if (bad || total > SW_FCAP) return 3;                // a level (or what one slice of it wins) exceeds the arrays
         // ---- D: the next level, in queue order
         const int nbase = base + fsz;
         for (int i = tid; i < nt; i += SW_THREADS) {
             const unsigned tk = s.tkey[i];
-            const int slot = s.off[tk >> SW_JBITS] + (int)(tk & ((1u << SW_JBITS) - 1u));
+            const int slot = slice_base + s.off[tk >> 19] + (int)(tk & ((1u << 19) - 1u));
             const int v = s.touched[i];
             const int q0 = __ldg(a.ptr + v), q1 = __ldg(a.ptr + v + 1);
             a.visit[nbase + slot] = v;
             a.lvl[v] = level + 1;
-            nr0[slot] = q0;
-            ndeg[slot] = q1 - q0;
+            nhr0[slot] = q0;
+            nhdeg[slot] = q1 - q0;
+        }
+        SW_T(8);
+        sw_cluster_sync();
+        SW_T(9);
+        // ---- E: the whole new level into this CTA's visited set
+        for (int i = tid; i < total; i += SW_THREADS) {
+            const int v = __ldcg(a.visit + nbase + i);
             atomicOr(s.bits + (v >> 5), 1u << (v & 31));
         }
         __syncthreads();
-        SW_T(4);
+        SW_T(10);
 #ifdef NGT_SW_CLOCKS
-        if (tid == 0) a.out->t[5] += 1;
+        if (tid == 0 && c == 0) a.out->t[11] += 1;
 #endif
         if (total == 0) break;
         base = nbase;
@@ -231,27 +294,30 @@ __device__ int sw_run(const SweepArgs &a, const SweepSmem &s, int start, int *co
     return visited == a.n ? 0 : 1;
 }
 
-__global__ void __launch_bounds__(SW_THREADS, 1) nd_sweep_kernel(SweepArgs a) {
+__global__ void __cluster_dims__(SW_CL, 1, 1) __launch_bounds__(SW_THREADS, 1) nd_sweep_kernel(SweepArgs a) {
     extern __shared__ __align__(16) unsigned char sw_raw[];
     SweepSmem s;
     s.best = reinterpret_cast<unsigned long long *>(sw_raw);
     s.ctr = reinterpret_cast<int *>(sw_raw + 8);
     s.wsum = reinterpret_cast<int *>(sw_raw + 32);
-    s.bits = reinterpret_cast<unsigned *>(s.wsum + 36);
-    s.r0 = reinterpret_cast<int *>(s.bits + a.nw);
-    s.deg = s.r0 + 2 * a.fcap;
-    s.off = s.deg + 2 * a.fcap;
-    s.touched = s.off + a.fcap;
-    s.tkey = reinterpret_cast<unsigned *>(s.touched + a.fcap);
+    s.tot = s.wsum + 36;
+    s.lr0 = s.tot + 4 * SW_CL;
+    s.ldeg = s.lr0 + SW_LP;
+    s.off = s.ldeg + SW_LP;
+    s.touched = s.off + SW_LP;
+    s.tkey = reinterpret_cast<unsigned *>(s.touched + SW_LT);
+    s.bits = s.tkey + SW_LT;
     const int tid = threadIdx.x;
+    const int c = sw_cluster_rank();
 #ifdef NGT_SW_CLOCKS
-    if (tid == 0) for (int i = 0; i < 6; ++i) a.out->t[i] = 0;
+    if (tid == 0 && c == 0) for (int i = 0; i < 12; ++i) a.out->t[i] = 0;
 #endif
     int count = 0, nlev = 0, lb = 0, ls = 0;
     int root = a.start < 0 ? 0 : a.start;
     int status = sw_run(a, s, root, &count, &nlev, &lb, &ls);
     if (a.start < 0 && status == 0) {
-        // minimum-degree node of the last level, the latest visited among equals (George & Liu's pseudo-peripheral step)
+        // minimum-degree node of the last level, the latest visited among equals (George & Liu's pseudo-peripheral
+        // step); every CTA works it out for itself
         if (tid == 0) *s.best = ~0ull;
         __syncthreads();
         for (int i = tid; i < ls; i += SW_THREADS) {
@@ -262,13 +328,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) nd_sweep_kernel(SweepArgs a) {
         }
         __syncthreads();
         const int best = __ldcg(a.visit + (int)(0xffffffffu - (unsigned)(*s.best & 0xffffffffull)));
-        __syncthreads();
+        sw_cluster_sync();                                   // nobody reads the first sweep's order any more
         if (best != 0) {
             root = best;
             status = sw_run(a, s, root, &count, &nlev, &lb, &ls);
         }
     }
-    if (tid == 0) {
+    if (tid == 0 && c == 0) {
         a.out->count = count;
         a.out->nlev = nlev;
         a.out->status = status;
@@ -283,6 +349,7 @@ struct SweepCtx {
     int *d_ptr = nullptr, *d_adj = nullptr, *d_lvl = nullptr, *d_visit = nullptr;
     unsigned *d_key = nullptr;
     SweepOut *d_out = nullptr, *h_out = nullptr;
+    int *d_hdr = nullptr;   // row extents of two levels
     size_t cap_n = 0, cap_adj = 0;
     void free_buffers() {
         cudaFree(d_ptr); cudaFree(d_adj); cudaFree(d_lvl); cudaFree(d_visit); cudaFree(d_key);
@@ -322,28 +389,22 @@ public:
     }
     ~GpuSweeps() override = default;   // contexts live as long as the process (the CUDA context may be gone at exit)
 
-    bool sweep(int32_t n, const int32_t *ptr, const int32_t *adj, int64_t nadj, int32_t start, int32_t *lvl,
-               int32_t *visit, int32_t *nlev) override {
-        if (broken_.load(std::memory_order_relaxed) || n < 2 || nadj <= 0 || nadj > 0x7fffffff) return false;
+    int sweep(int32_t n, const int32_t *ptr, const int32_t *adj, int64_t nadj, int32_t start, int32_t *lvl,
+              int32_t *visit, int32_t *nlev) override {
+        if (broken_.load(std::memory_order_relaxed) || n < 2 || nadj <= 0 || nadj > 0x7fffffff) return -1;
         const int nw = (n + 31) / 32;
-        if (max_degree(n, ptr) >= (1 << 19)) return false;   // claims hold 19 bits of row position
-        const long long fixed = 32 + 36 * 4 + (long long)nw * 4;   // scalars, scan scratch, bitmap
-        long long fcap = (SW_SMEM_LIMIT - fixed) / 28;
-        if (fcap < 1024) return false;                       // the bitmap does not fit beside the per-parent arrays
-        if (fcap > SW_FCAP_MAX) fcap = SW_FCAP_MAX;
-        // levels of a d-dimensional structure hold ~n^(1-1/d) nodes; what shared memory the arrays leave becomes L1,
-        // which then holds the rows of a level between the four-entry steps of their threads
-        const long long want = std::max(2048LL, (long long)(10.0 * std::sqrt((double)n)));
-        if (!big_levels_.load(std::memory_order_relaxed) && fcap > want) fcap = want;
-        const size_t smem = (size_t)(fixed + fcap * 28);
+        if (max_degree(n, ptr) >= (1 << SW_JBITS) - 1) return -1;   // claims hold 18 bits of row position
+        const size_t smem = 32 + (36 + 4 * SW_CL) * 4 + (3 * (size_t)SW_LP + 2 * (size_t)SW_LT) * 4 + (size_t)nw * 4;
+        if (smem > (size_t)SW_SMEM_LIMIT) return -1;      // the visited set does not fit in shared memory
         SweepCtx *c = acquire();
-        if (!c) return false;
+        if (!c) return 0;
         bool ok = false;
         do {
             if (cudaSetDevice(device_) != cudaSuccess) break;
             if (!c->st) {
                 if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) break;
                 if (cudaMalloc(&c->d_out, sizeof(SweepOut)) != cudaSuccess) break;
+                if (cudaMalloc(&c->d_hdr, 4 * (size_t)SW_FCAP * sizeof(int)) != cudaSuccess) break;
                 if (cudaMallocHost(&c->h_out, sizeof(SweepOut)) != cudaSuccess) break;
             }
             if (!attr_set_.load(std::memory_order_acquire)) {
@@ -356,6 +417,7 @@ public:
             if (cudaMemcpyAsync(c->d_ptr, ptr, ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice, c->st) != cudaSuccess) break;
             if (cudaMemcpyAsync(c->d_adj, adj, (size_t)nadj * sizeof(int), cudaMemcpyHostToDevice, c->st) != cudaSuccess) break;
             g_sw_h2d += (long long)(((size_t)n + 1 + (size_t)nadj) * sizeof(int));
+            uploads.fetch_add(1, std::memory_order_release);   // the engine holds its own bulk copies back until here
             auto t1 = t0;
             if (trace) { cudaStreamSynchronize(c->st); t1 = std::chrono::steady_clock::now(); }
             SweepArgs a;
@@ -368,17 +430,17 @@ public:
             a.visit = c->d_visit;
             a.out = c->d_out;
             a.nw = nw;
-            a.fcap = (int)fcap;
-            nd_sweep_kernel<<<1, SW_THREADS, smem, c->st>>>(a);
+            a.hr0 = c->d_hdr;
+            a.hdeg = c->d_hdr + 2 * SW_FCAP;
+            nd_sweep_kernel<<<SW_CL, SW_THREADS, smem, c->st>>>(a);
             if (cudaGetLastError() != cudaSuccess) break;
             if (cudaMemcpyAsync(c->h_out, c->d_out, sizeof(SweepOut), cudaMemcpyDeviceToHost, c->st) != cudaSuccess) break;
             if (cudaStreamSynchronize(c->st) != cudaSuccess) break;
             g_sw_d2h += (long long)sizeof(SweepOut);
             const auto t2 = std::chrono::steady_clock::now();
             if (c->h_out->status != 0) {                     // a property of the graph, not an error: the host sweeps
-                if (c->h_out->status == 3) big_levels_.store(true, std::memory_order_relaxed);   // next time: all the room
                 release(c);
-                return false;
+                return -1;
             }
             if (cudaMemcpyAsync(lvl, c->d_lvl, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->st) != cudaSuccess) break;
             if (cudaMemcpyAsync(visit, c->d_visit, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->st) != cudaSuccess) break;
@@ -394,8 +456,10 @@ public:
                              n, start, c->h_out->nlev, ms(t0, t1), ms(t1, t2), ms(t2, std::chrono::steady_clock::now()));
 #ifdef NGT_SW_CLOCKS
                 const long long *t = c->h_out->t;
-                std::fprintf(stderr, "[ngt timing]       cycles: init %lld  claims %lld  winners %lld  scan %lld  append %lld  over %lld levels\n",
-                             t[0], t[1], t[2], t[3], t[4], t[5]);
+                const double L = (double)std::max(1LL, t[11]);
+                std::fprintf(stderr, "[ngt timing]       cycles per level over %lld levels: (%.0f %.0f) claims %.0f  barrier %.0f  winners %.0f  "
+                             "scan+publish %.0f  barrier %.0f  place %.0f  barrier %.0f  visited set %.0f   (init %lld)\n",
+                             t[11], t[1] / L, t[2] / L, t[3] / L, t[4] / L, t[5] / L, t[6] / L, t[7] / L, t[8] / L, t[9] / L, t[10] / L, t[0]);
 #endif
             }
         } while (false);
@@ -406,7 +470,7 @@ public:
             broken_.store(true, std::memory_order_relaxed);
         }
         release(c);
-        return ok;
+        return ok ? 1 : -1;
     }
 
     void release_buffers() {
@@ -447,7 +511,7 @@ private:
     int device_;
     std::mutex mu_;
     std::vector<std::unique_ptr<Slot> > all_;
-    std::atomic<bool> broken_{false}, big_levels_{false};
+    std::atomic<bool> broken_{false};
     std::atomic<bool> attr_set_{false};
 };
 

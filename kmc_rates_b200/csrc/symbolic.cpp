@@ -195,19 +195,21 @@ struct Dissector {
     // sweeps of large subgraphs go to the accelerator when the engine supplied one (same queue order, so the same
     // ordering); a graph it keeps declining (not connected, thin levels) stops being offered
     SweepAccel *accel = nullptr;
+    int32_t accel_min = 0;
     std::atomic<int> accel_declined{0};
     bool offer(const Sub &G) const {
-        return accel && G.n >= accel->min_nodes && accel_declined.load(std::memory_order_relaxed) < 2;
+        return accel && G.n >= accel_min && accel_declined.load(std::memory_order_relaxed) < 2;
     }
     bool accel_sweep(const Sub &G, int32_t start, std::vector<int32_t> &lvl, std::vector<int32_t> &visit, int32_t &nlev) {
         lvl.resize(G.n);
         visit.resize(G.n);
         int32_t nl = 0;
-        if (accel->sweep(G.n, G.ptr.data(), G.adj.data(), (int64_t)G.adj.size(), start, lvl.data(), visit.data(), &nl)) {
+        const int r = accel->sweep(G.n, G.ptr.data(), G.adj.data(), (int64_t)G.adj.size(), start, lvl.data(), visit.data(), &nl);
+        if (r == 1) {
             nlev = nl;
             return true;
         }
-        accel_declined.fetch_add(1, std::memory_order_relaxed);
+        if (r < 0) accel_declined.fetch_add(1, std::memory_order_relaxed);
         visit.clear();
         return false;
     }
@@ -668,7 +670,7 @@ void analyse_dense(int64_t n, const std::vector<int64_t> &A, const std::vector<i
 
 void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
                     const std::vector<int64_t> &A, const std::vector<int64_t> &B,
-                    int leaf_size, Symbolic &S, SweepAccel *accel) {
+                    int leaf_size, Symbolic &S, SweepAccel *accel, int32_t accel_min_nodes) {
     S = Symbolic();
     const int64_t n = g.n;
     S.n = n;
@@ -686,6 +688,7 @@ void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
     Timer tm;
     Dissector D(leaf_size > 0 ? leaf_size : 64);
     D.accel = accel;
+    D.accel_min = accel_min_nodes > 0 ? accel_min_nodes : (accel ? accel->min_nodes : 0);
     // top-level subgraph: the rate graph induced on the intermediates (A ∪ B and absent nodes are left out, so
     // the dissector never walks through them)
     Sub top;

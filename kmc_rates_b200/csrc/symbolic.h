@@ -12,6 +12,7 @@
 // No arithmetic happens here; the numeric phase never allocates.
 #pragma once
 #include <chrono>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -115,11 +116,14 @@ struct SweepAccel {
     // CSR subgraph (local ids, symmetric, no self loops, rows without duplicates).
     // start >= 0: one sweep from `start`.  start < 0: pseudo-peripheral search -- sweep from node 0, pick the
     // minimum-degree node of the last level (the latest visited among equals) and, unless that is node 0, sweep again
-    // from it.  Fills lvl[n], visit[n], *nlev and returns true; returns false when it declines (size limits, no free
-    // context, graph not connected, levels too thin to pay off, device error): the caller sweeps on the host.
-    virtual bool sweep(int32_t n, const int32_t *ptr, const int32_t *adj, int64_t nadj, int32_t start, int32_t *lvl,
+    // from it.  Fills lvl[n], visit[n], *nlev and returns 1.  Otherwise the caller sweeps on the host: 0 = not now (no
+    // free context), -1 = not this graph (size limits, not connected, levels too thin to pay off, device error).
+    virtual int sweep(int32_t n, const int32_t *ptr, const int32_t *adj, int64_t nadj, int32_t start, int32_t *lvl,
                        int32_t *visit, int32_t *nlev) = 0;
-    int32_t min_nodes = 24576;   // smaller subgraphs are swept on the host (copy + launch cost more than the sweep)
+    int32_t min_nodes = 65536;   // smaller subgraphs are swept on the host: a level costs the kernel ~10 us whatever its
+                                 // size, a host core ~2.6 ns per adjacency entry (measured break-even ~7e4 nodes of the
+                                 // 2-D landscapes); NGT_B200_GPU_SWEEP_MIN or ngt_options.sweep_min_nodes override it
+    std::atomic<int> uploads{0}; // subgraphs copied to the accelerator so far (the engine orders its own copies after the first)
 };
 
 // Sparse network: nested dissection + supernodal symbolic factorisation.
@@ -127,7 +131,7 @@ struct SweepAccel {
 // creates nodes named by a rate, ngt.hpp:114-117).
 void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
                     const std::vector<int64_t> &A, const std::vector<int64_t> &B,
-                    int leaf_size, Symbolic &S, SweepAccel *accel = nullptr);
+                    int leaf_size, Symbolic &S, SweepAccel *accel = nullptr, int32_t accel_min_nodes = 0);
 
 // Complete network: one front holding every intermediate, plus the root.
 void analyse_dense(int64_t n, const std::vector<int64_t> &A, const std::vector<int64_t> &B, Symbolic &S);

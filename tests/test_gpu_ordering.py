@@ -120,11 +120,12 @@ def test_sweep_declines_what_it_cannot_do():
     assert nlev == 40 and visit[0] == 39 and lvl[0] == 39
 
 
-@pytest.mark.parametrize("side,nodes_min", [(180, None)])
-def test_elimination_order_does_not_depend_on_who_sweeps(side, nodes_min):
-    """32 400 minima: the two largest subgraphs of the dissection are above the device threshold"""
+@pytest.mark.parametrize("side,sweep_min", [(120, 2000), (180, 8000)])
+def test_elimination_order_does_not_depend_on_who_sweeps(side, sweep_min):
+    """the threshold is lowered so that several levels of the dissection (both halves of a split, concurrently)
+    are swept on the device"""
     n, src, dst, k, A, B = synth.landscape_2d(side, T=0.3, seed=4)
-    dev = Handle.from_coo(n, src, dst, k, A, B)
+    dev = Handle.from_coo(n, src, dst, k, A, B, sweep_min_nodes=sweep_min)
     host = Handle.from_coo(n, src, dst, k, A, B, host_sweeps=1)
     assert np.array_equal(dev.elimination_order(), host.elimination_order())
     dev.compute_rates()
