@@ -289,40 +289,54 @@ struct Dissector {
     // induced by a team of threads (count, prefix, fill: every member's slice of the adjacency has one writer, so the
     // result is the serial one bit for bit): at the top of the dissection only one or two branches exist and the other
     // cores idle, while these passes over the whole adjacency were ~40 % of the critical path of the ordering.
-    static void induce(const Sub &G, const std::vector<int32_t> &members, std::vector<int32_t> &newid, Sub &H, int nthreads = 1) {
+    static void induce(const Sub &G, const std::vector<int32_t> &members, std::vector<int32_t> &newid, Sub &H, int nthreads = 1,
+                       bool reset = true) {
         H.n = (int32_t)members.size();
         H.glob.resize(H.n);
         H.ptr.assign(H.n + 1, 0);
         const int32_t *adj = G.adj.data();
         const int32_t last = (int32_t)G.adj.size() - 1;
         if (nthreads > 1 && H.n >= 8192) {
+            // every thread filters the rows of its slice of the members into a buffer of its own (one look-up per
+            // adjacency entry; counting first and filling afterwards looked every entry up twice), then the buffers are
+            // laid end to end
             const int T = nthreads;
+            std::vector<std::vector<int32_t> > buf(T);
+            std::vector<int64_t> tot(T + 1, 0);
             parallel_ranges(T, H.n, [&](int, int64_t i0, int64_t i1) {
                 for (int64_t i = i0; i < i1; ++i) newid[members[i]] = (int32_t)i;
             });
-            parallel_ranges(T, H.n, [&](int, int64_t i0, int64_t i1) {
-                for (int64_t i = i0; i < i1; ++i) {
-                    const int32_t v = members[i];
-                    int32_t c = 0;
-                    for (int32_t e = G.ptr[v]; e < G.ptr[v + 1]; ++e) c += newid[adj[e]] >= 0;
-                    H.ptr[i + 1] = c;
-                }
-            });
-            for (int32_t i = 0; i < H.n; ++i) H.ptr[i + 1] += H.ptr[i];
-            H.adj.resize(H.ptr[H.n]);
-            parallel_ranges(T, H.n, [&](int, int64_t i0, int64_t i1) {
+            parallel_ranges(T, H.n, [&](int t, int64_t i0, int64_t i1) {
+                size_t cap = 0;
+                for (int64_t i = i0; i < i1; ++i) cap += (size_t)(G.ptr[members[i] + 1] - G.ptr[members[i]]);
+                std::vector<int32_t> &b = buf[t];
+                b.resize(cap);
+                int32_t *w = b.data();
                 for (int64_t i = i0; i < i1; ++i) {
                     const int32_t v = members[i];
                     H.glob[i] = G.glob[v];
-                    int32_t w = H.ptr[i];
+                    if (i + 4 < i1) __builtin_prefetch(adj + G.ptr[members[i + 4]]);
+                    const int32_t *w0 = w;
                     for (int32_t e = G.ptr[v]; e < G.ptr[v + 1]; ++e) {
+                        __builtin_prefetch(&newid[adj[std::min(e + 8, last)]]);
                         const int32_t x = newid[adj[e]];
-                        if (x >= 0) H.adj[w++] = x;
+                        if (x >= 0) *w++ = x;
                     }
+                    H.ptr[i + 1] = (int32_t)(w - w0);        // row length for now
                 }
+                tot[t + 1] = w - b.data();
             });
-            parallel_ranges(T, H.n, [&](int, int64_t i0, int64_t i1) {
-                for (int64_t i = i0; i < i1; ++i) newid[members[i]] = -1;
+            for (int t = 0; t < T; ++t) tot[t + 1] += tot[t];
+            H.adj.resize((size_t)tot[T]);
+            parallel_ranges(T, H.n, [&](int t, int64_t i0, int64_t i1) {
+                int32_t run = (int32_t)tot[t];
+                for (int64_t i = i0; i < i1; ++i) {
+                    run += H.ptr[i + 1];
+                    H.ptr[i + 1] = run;
+                }
+                std::copy(buf[t].begin(), buf[t].begin() + (tot[t + 1] - tot[t]), H.adj.begin() + tot[t]);
+                if (reset)
+                    for (int64_t i = i0; i < i1; ++i) newid[members[i]] = -1;
             });
             return;
         }
@@ -478,7 +492,7 @@ struct Dissector {
                 Sub H2;
                 {
                     std::vector<int32_t> newid(G.n, -1);
-                    induce(G, P2, newid, H2, team_threads(depth));
+                    induce(G, P2, newid, H2, team_threads(depth), false);
                 }
                 dissect(H2, o2, depth + 1);
                 running.fetch_sub(1, std::memory_order_relaxed);
@@ -487,7 +501,7 @@ struct Dissector {
                 Sub H1;
                 {
                     std::vector<int32_t> newid(G.n, -1);
-                    induce(G, P1, newid, H1, team_threads(depth));
+                    induce(G, P1, newid, H1, team_threads(depth), false);
                 }
                 dissect(H1, out, depth + 1, &lvl1);
             }
@@ -698,27 +712,38 @@ void analyse_sparse(const Adjacency &g, const std::vector<char> &present,
         top.glob = inter;
         for (int32_t i = 0; i < top.n; ++i) newid[inter[i]] = i;
         top.ptr.assign(top.n + 1, 0);
-        // count, prefix, fill: every node's slice of the adjacency is written by one thread
+        // every thread filters the rows of its slice of the intermediates into a buffer of its own (one look-up per
+        // adjacency entry), then the buffers are laid end to end
         const int T = top.n < 20000 ? 1 : (int)std::min(host_threads(), 8u);
-        parallel_ranges(T, top.n, [&](int /*t*/, int64_t i0, int64_t i1) {
+        std::vector<std::vector<int32_t> > buf(T);
+        std::vector<int64_t> tot(T + 1, 0);
+        parallel_ranges(T, top.n, [&](int t, int64_t i0, int64_t i1) {
+            size_t cap = 0;
+            for (int64_t i = i0; i < i1; ++i) cap += (size_t)(g.ptr[inter[i] + 1] - g.ptr[inter[i]]);
+            std::vector<int32_t> &b = buf[t];
+            b.resize(cap);
+            int32_t *w = b.data();
             for (int64_t i = i0; i < i1; ++i) {
                 const int32_t u = inter[i];
-                int32_t c = 0;
-                for (int64_t e = g.ptr[u]; e < g.ptr[u + 1]; ++e) c += newid[g.adj[e]] >= 0;
-                top.ptr[i + 1] = c;
-            }
-        });
-        for (int32_t i = 0; i < top.n; ++i) top.ptr[i + 1] += top.ptr[i];
-        top.adj.resize(top.ptr[top.n]);
-        parallel_ranges(T, top.n, [&](int /*t*/, int64_t i0, int64_t i1) {
-            for (int64_t i = i0; i < i1; ++i) {
-                const int32_t u = inter[i];
-                int32_t w = top.ptr[i];
+                const int32_t *w0 = w;
                 for (int64_t e = g.ptr[u]; e < g.ptr[u + 1]; ++e) {
                     const int32_t x = newid[g.adj[e]];
-                    if (x >= 0) top.adj[w++] = x;
+                    if (x >= 0) *w++ = x;
                 }
+                top.ptr[i + 1] = (int32_t)(w - w0);          // row length for now
             }
+            tot[t + 1] = w - b.data();
+        });
+        for (int t = 0; t < T; ++t) tot[t + 1] += tot[t];
+        if (tot[T] > 0x7fffffffLL) throw std::length_error("symbolic: more than 2^31 adjacency entries");
+        top.adj.resize((size_t)tot[T]);
+        parallel_ranges(T, top.n, [&](int t, int64_t i0, int64_t i1) {
+            int32_t run = (int32_t)tot[t];
+            for (int64_t i = i0; i < i1; ++i) {
+                run += top.ptr[i + 1];
+                top.ptr[i + 1] = run;
+            }
+            std::copy(buf[t].begin(), buf[t].begin() + (tot[t + 1] - tot[t]), top.adj.begin() + tot[t]);
         });
     }
     tm.lap("top-level subgraph");
