@@ -77,3 +77,21 @@ def test_analysis_of_disconnected_and_irregular_graph(analysis_bench, tmp_path):
     serial = _hashes(analysis_bench, graph, {"NGT_B200_HOST_THREADS": "1", "NGT_B200_ND_THREADS_DEPTH": "0"}, reps=1)
     threaded = _hashes(analysis_bench, graph, {"NGT_B200_HOST_THREADS": "8", "NGT_B200_ND_THREADS_DEPTH": "4"}, reps=2)
     assert len(set(serial + threaded)) == 1, (serial, threaded)
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_analysis_does_not_depend_on_who_sweeps(analysis_bench, tmp_path, mode):
+    """the dissector hands the sweeps of large subgraphs to an accelerator (the CUDA kernel of csrc/ordering.cu in the
+    product; here a host stand-in behind the same interface, mode 2 declining every third call): same structure"""
+    sys.path.insert(0, ROOT)
+    from kmc_rates_b200 import synth
+    n, src, dst, _k, A, B = synth.landscape_2d(90, T=0.3, seed=2)
+    graph = str(tmp_path / "g.bin")
+    _dump(graph, n, src, dst, A, B)
+    host = _hashes(analysis_bench, graph, {"NGT_B200_HOST_THREADS": "4"}, reps=1)
+    env = dict(os.environ, NGT_B200_HOST_THREADS="4", NGT_ANALYSIS_MOCK_ACCEL=mode)
+    out = subprocess.run([analysis_bench, graph, "1"], env=env, check=True, capture_output=True, text=True).stdout
+    accel = [line.split()[-1] for line in out.splitlines() if "structure hash" in line]
+    offered = [int(line.split()[2]) for line in out.splitlines() if "sweeps offered" in line]
+    assert offered and offered[0] >= 4, out
+    assert host == accel, (host, accel)
