@@ -46,10 +46,8 @@ struct SweepOut {
 };
 #ifdef NGT_SW_CLOCKS
 #define SW_T(i) do { if (threadIdx.x == 0 && c == 0) { const long long c_ = clock64(); a.out->t[i] += c_ - t_last; t_last = c_; } } while (0)
-#define SW_TD(i, dep) do { if (threadIdx.x == 0 && c == 0) { const long long c_ = clock64() + ((dep) == -12345 ? 1 : 0); a.out->t[i] += c_ - t_last; t_last = c_; } } while (0)
 #else
 #define SW_T(i) do { } while (0)
-#define SW_TD(i, dep) do { } while (0)
 #endif
 
 struct SweepArgs {
@@ -457,9 +455,9 @@ public:
 #ifdef NGT_SW_CLOCKS
                 const long long *t = c->h_out->t;
                 const double L = (double)std::max(1LL, t[11]);
-                std::fprintf(stderr, "[ngt timing]       cycles per level over %lld levels: (%.0f %.0f) claims %.0f  barrier %.0f  winners %.0f  "
+                std::fprintf(stderr, "[ngt timing]       cycles per level over %lld levels: claims %.0f  barrier %.0f  winners %.0f  "
                              "scan+publish %.0f  barrier %.0f  place %.0f  barrier %.0f  visited set %.0f   (init %lld)\n",
-                             t[11], t[1] / L, t[2] / L, t[3] / L, t[4] / L, t[5] / L, t[6] / L, t[7] / L, t[8] / L, t[9] / L, t[10] / L, t[0]);
+                             t[11], t[3] / L, t[4] / L, t[5] / L, t[6] / L, t[7] / L, t[8] / L, t[9] / L, t[10] / L, t[0]);
 #endif
             }
         } while (false);
