@@ -539,12 +539,16 @@ def same_size_object(torch, Handle, cores, side, ref_value, ref_rates, device):
     Handle.from_coo(n, src, dst, k, A, B, device=device).close()        # warm the host workspace for this size
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    got = []
+    got, each = [], []
     for (n, src, dst, k, A, B) in nets:
+        ta = time.perf_counter()
         g = Handle.from_coo(n, src, dst, k, A, B, device=device)
+        tb = time.perf_counter()
         g.compute_rates()
         got.append(np.array(g.rates()))
+        tc = time.perf_counter()
         g.close()
+        each.append([round(1e3 * (tb - ta), 2), round(1e3 * (tc - tb), 2), round(1e3 * (time.perf_counter() - tc), 2)])
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
     nodes = sum(x[0] - 2 for x in nets)
@@ -552,6 +556,7 @@ def same_size_object(torch, Handle, cores, side, ref_value, ref_rates, device):
             "gpu_e2e_nodes_per_s": nodes / sec, "gpu_e2e_ms_per_network": 1e3 * sec / cores,
             "reference_nodes_per_s": ref_value, "ratio_gpu_e2e_over_reference": nodes / sec / ref_value,
             "max_rel_err_vs_reference": rel(np.array(got), np.array(ref_rates)),
+            "ms_create_compute_close_each": each,
             "note": "same generator, seeds and sizes in both arms; the reference runs its %d networks concurrently on %d "
                     "cores, the GPU arm runs them one after the other through the public end-to-end call" % (cores, cores)}
 

@@ -58,13 +58,42 @@ struct NumericError : std::runtime_error {
 // Process-wide cache of device allocations.  cudaMalloc / cudaFree of the multi-hundred-MB front pools cost up to
 // ~100 ms each (cudaFree also synchronises the device); a sweep that creates and destroys handles would pay that per
 // network.  Freed blocks are kept (up to a cap) and handed back to the next handle on the same device.
+// under NGT_B200_TIMING: runtime calls that stall (a cudaMalloc that has to map new memory, a copy behind other work)
+struct SlowCall {
+    const char *what;
+    size_t bytes;
+    std::chrono::steady_clock::time_point t0;
+    static bool on() {
+        static const bool v = std::getenv("NGT_B200_TIMING") != nullptr;
+        return v;
+    }
+    SlowCall(const char *w, size_t b) : what(w), bytes(b) { if (on()) t0 = std::chrono::steady_clock::now(); }
+    ~SlowCall() {
+        if (!on()) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 2.0) std::fprintf(stderr, "[ngt timing]     slow call: %s of %zu bytes took %.2f ms\n", what, bytes, ms);
+    }
+};
+
 struct DevCache {
     std::mutex mu;
     std::multimap<std::pair<int, size_t>, void *> blocks;   // (device, bytes) -> pointer
     size_t cached = 0;
     static constexpr size_t CAP = (size_t)24 << 30;
 
+    // Requests are rounded up to size classes (four per octave below 256 MB, 2 MB steps above) so that handles of
+    // similar networks find each other's blocks: a cudaMalloc of a size the process has not used before occasionally
+    // takes 20-90 ms on these boxes (seen for 2 MB blocks), which tripled the cost of a 5 ms small-network build.
+    static size_t size_class(size_t bytes) {
+        if (bytes <= ((size_t)64 << 10)) return (size_t)64 << 10;
+        if (bytes >= ((size_t)256 << 20)) return (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+        size_t top = (size_t)1 << 16;
+        while ((top << 1) <= bytes) top <<= 1;
+        const size_t step = top >> 2;
+        return (bytes + step - 1) / step * step;
+    }
     void *get(size_t bytes, size_t &cap) {
+        bytes = size_class(bytes);
         int dev = 0;
         cudaGetDevice(&dev);
         {
@@ -79,6 +108,7 @@ struct DevCache {
             }
         }
         void *p = nullptr;
+        SlowCall sc("cudaMalloc", bytes);
         cudaError_t e = cudaMalloc(&p, bytes);
         if (e != cudaSuccess) {
             trim();   // give cached memory back and retry once
@@ -94,6 +124,7 @@ struct DevCache {
         cudaGetDevice(&dev);
         std::lock_guard<std::mutex> lk(mu);
         if (cached + cap > CAP) {
+            SlowCall sc("cudaFree (cache full)", cap);
             cudaFree(p);
             return;
         }
@@ -104,6 +135,7 @@ struct DevCache {
         std::lock_guard<std::mutex> lk(mu);
         int cur = 0;
         cudaGetDevice(&cur);
+        SlowCall sc("cache trim", cached);
         for (auto &kv : blocks) {
             cudaSetDevice(kv.first.first);
             cudaFree(kv.second);
@@ -142,6 +174,7 @@ struct DevBuf {
     void upload(const std::vector<T> &v) {
         alloc(v.size());
         if (!v.empty()) {
+            SlowCall sc("cudaMemcpy (upload)", v.size() * sizeof(T));
             CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
             g_h2d_bytes += (long long)(v.size() * sizeof(T));
         }
@@ -1720,6 +1753,7 @@ void build_sparse(Engine *E, int64_t n, int64_t nnz, const int64_t *src, const i
         if (all_present && !was_pruned && kept_entries == nnz) {
             // ---- rate -> slot table on the device (no duplicates, nothing absent or pruned: row u = node u) ----------
             structure_task.finish();
+            tm.lap("structure upload + pools (joined)");
             CK(cudaSetDevice(E->device));
             std::vector<int> ffirst(S.fronts.size());
             for (size_t i = 0; i < S.fronts.size(); ++i) ffirst[i] = S.fronts[i].first;
