@@ -46,6 +46,9 @@ def test_analysis_is_independent_of_thread_count(analysis_bench, tmp_path, side)
     threaded = _hashes(analysis_bench, graph, {"NGT_B200_HOST_THREADS": "8", "NGT_B200_ND_THREADS_DEPTH": "4"})
     assert len(serial) == 2 and len(threaded) == 2
     assert len(set(serial + threaded)) == 1, (serial, threaded)
+    # the sweeps have a scalar and (on hosts that support it) an AVX-512 version: same visiting order
+    scalar = _hashes(analysis_bench, graph, {"NGT_B200_HOST_THREADS": "4", "NGT_B200_NO_AVX512": "1"}, reps=1)
+    assert scalar[0] == serial[0], (scalar, serial)
 
 
 def test_analysis_of_disconnected_and_irregular_graph(analysis_bench, tmp_path):
@@ -77,6 +80,11 @@ def test_analysis_of_disconnected_and_irregular_graph(analysis_bench, tmp_path):
     serial = _hashes(analysis_bench, graph, {"NGT_B200_HOST_THREADS": "1", "NGT_B200_ND_THREADS_DEPTH": "0"}, reps=1)
     threaded = _hashes(analysis_bench, graph, {"NGT_B200_HOST_THREADS": "8", "NGT_B200_ND_THREADS_DEPTH": "4"}, reps=2)
     assert len(set(serial + threaded)) == 1, (serial, threaded)
+    # the same through the accelerator interface (stand-in on the host): components, the clique and the chain are
+    # declined or handed back, the structure stays the same
+    for mode in ("1", "2"):
+        accel = _hashes(analysis_bench, graph, {"NGT_B200_HOST_THREADS": "4", "NGT_ANALYSIS_MOCK_ACCEL": mode}, reps=1)
+        assert accel == serial, (mode, accel, serial)
 
 
 @pytest.mark.parametrize("mode", ["1", "2"])
