@@ -7,7 +7,7 @@
 // that lead to it, so every entry (p, j) of the frontier that leads to an unvisited node v claims it with
 // atomicMin(key[v], p << 18 | j), the claim that stands is the winner, and winners are placed at (exclusive scan of the
 // winners per parent) + (rank inside the parent's row).  See sw_run for the phases.
-// The kernel gives up (status 2) on structures thinner than ~24 nodes per level: a level costs it ~4 us whatever its
+// The kernel gives up (status 2) on structures thinner than ~24 nodes per level: a level costs it ~10 us whatever its
 // size, a host core ~2.6 ns per adjacency entry.
 #include "ordering.h"
 
@@ -167,12 +167,12 @@ __device__ __forceinline__ void sw_win_chunk(const SweepArgs &a, const SweepSmem
 }
 
 // One sweep from `start` by the whole cluster; every return value is uniform over the cluster.  A level's nodes (the
-// "parents") are split into SW_CL contiguous slices, one per CTA, one thread per parent, eight row entries in flight:
+// "parents") are split into SW_CL contiguous slices, one per CTA, one thread per parent, up to 32 row entries in flight:
 //   A  an entry (p, j) that leads to an unvisited node v claims it: atomicMin(key[v], p << 18 | j), no return value;
 //   B  the same walk again: the entry whose claim stands is the winner.  A thread meets its parent's winners in row
 //      order, so the rank of a winner inside its parent is a running count; winners go on the CTA's `touched` list;
-//   C  exclusive scan of the winners per parent inside the slice; the slices' totals are exchanged through global
-//      memory, which gives every CTA the offset of its slice in the next level;
+//   C  exclusive scan of the winners per parent inside the slice; the slices' totals are exchanged through distributed
+//      shared memory, which gives every CTA the offset of its slice in the next level;
 //   D  one thread per touched node: position = slice offset + parent offset + rank; level and row extent to global
 //      memory;
 //   E  every CTA sets the bits of the whole new level in its own copy of the visited set.
