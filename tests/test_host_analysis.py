@@ -85,6 +85,9 @@ def test_analysis_of_disconnected_and_irregular_graph(analysis_bench, tmp_path):
     for mode in ("1", "2"):
         accel = _hashes(analysis_bench, graph, {"NGT_B200_HOST_THREADS": "4", "NGT_ANALYSIS_MOCK_ACCEL": mode}, reps=1)
         assert accel == serial, (mode, accel, serial)
+    # scalar sweeps and row filters against the AVX-512 ones (rows of every length from 1 to 59 and beyond)
+    scalar = _hashes(analysis_bench, graph, {"NGT_B200_HOST_THREADS": "4", "NGT_B200_NO_AVX512": "1"}, reps=1)
+    assert scalar == serial, (scalar, serial)
 
 
 @pytest.mark.parametrize("mode", ["1", "2"])
